@@ -1,0 +1,385 @@
+// Shared host/device helpers of the ccg library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ccg.h"
+
+namespace ccg {
+
+// --------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------
+struct NcclApi;  // dlopen'ed entry points (ctx.cu)
+
+}  // namespace ccg
+
+struct ccg_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t global_mem = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  int64_t launches = 0;
+  // multi-GPU
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  // pinned scratch for small D2H polls
+  int* h_poll = nullptr;
+  // event pool for opts.profile
+  std::vector<cudaEvent_t> events;
+};
+
+namespace ccg {
+
+int set_error(ccg_ctx* ctx, int status, const char* what, cudaError_t e = cudaSuccess);
+
+#define CCG_CUDA(ctx, call)                                              \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) return ::ccg::set_error((ctx), CCG_ERR_CUDA, #call, e__); \
+  } while (0)
+
+int nccl_allreduce_sum(ccg_ctx* ctx, double* buf, size_t count);
+
+// --------------------------------------------------------------------------
+// LM state machine shared by the single-camera and the rig solver.  It lives
+// in global memory, one per problem, and is advanced only by device code: the
+// host enqueues a fixed kernel sequence per iteration and never reads it back
+// until the loop ends (it polls one counter every few iterations).
+// --------------------------------------------------------------------------
+struct LmParams {
+  int max_iterations;
+  double initial_radius, max_radius, min_radius;
+  double min_relative_decrease;
+  double min_diagonal, max_diagonal;
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double huber_a;
+  double noise_factor;
+};
+
+inline LmParams to_params(const ccg_opts& o) {
+  LmParams p;
+  p.max_iterations = o.max_iterations;
+  p.initial_radius = o.initial_radius;
+  p.max_radius = o.max_radius;
+  p.min_radius = o.min_radius;
+  p.min_relative_decrease = o.min_relative_decrease;
+  p.min_diagonal = o.min_diagonal;
+  p.max_diagonal = o.max_diagonal;
+  p.function_tolerance = o.function_tolerance;
+  p.gradient_tolerance = o.gradient_tolerance;
+  p.parameter_tolerance = o.parameter_tolerance;
+  p.huber_a = o.huber_a;
+  p.noise_factor = o.noise_factor;
+  return p;
+}
+
+constexpr int kHist = 48;
+constexpr int kBlindSteps = 2;  // sub-resolution (unvalidatable) steps taken before stopping
+
+struct LmState {
+  double cost;       // at the current (accepted) point
+  double cost0;      // at the initial point
+  double radius, nu, lambda;
+  double gTd_u, dDd_u;  // reduced-parameter share of g'd and d'Dd (written by the reduced solve)
+  double grad_norm;     // sqrt(g' D^-1 g)/sqrt(2 cost) at the current point
+  double n_obs;         // observations (global over ranks)
+  double sumsq;         // raw sum ||r||^2 at the current point (RMS)
+  double meas_scale;    // max |measurement| (sets the rounding noise of the cost)
+  int par;              // which of the two per-view buffers holds the current point
+  int status;           // 0 = running, else termination code
+  int first;            // the next sweep evaluates the initial point
+  int solve_ok;         // the last linear solve produced a candidate
+  int finalize;         // finished this iteration: one more gradient-norm pass is pending
+  int iterations, accepted, rejected, sweeps;
+  int blind;            // sub-resolution steps taken so far (at most kBlindSteps)
+  int n_hist;
+  // per-evaluation trace (ring of the last kHist sweeps): cost, candidate cost,
+  // gain ratio, radius used, relative step norm, accepted flag
+  double hist[kHist][6];
+};
+
+__host__ __device__ inline void lm_init(LmState& s, const LmParams& P) {
+  s.cost = 0.0;
+  s.cost0 = 0.0;
+  s.radius = P.initial_radius;
+  s.nu = 2.0;
+  s.lambda = 1.0 / P.initial_radius;
+  s.gTd_u = 0.0;
+  s.dDd_u = 0.0;
+  s.grad_norm = 0.0;
+  s.n_obs = 0.0;
+  s.sumsq = 0.0;
+  s.par = 0;
+  s.status = 0;
+  s.first = 1;
+  s.solve_ok = 1;
+  s.finalize = 0;
+  s.iterations = s.accepted = s.rejected = s.sweeps = 0;
+  s.blind = 0;
+  s.n_hist = 0;
+}
+
+#ifdef __CUDACC__
+
+// relative cost noise tolerated when a final sub-resolution step is taken
+constexpr double kCostNoise = 1e-12;
+
+__device__ __forceinline__ double clampd(double x, double lo, double hi) {
+  return fmin(fmax(x, lo), hi);
+}
+
+__device__ inline void lm_finish(LmState& s, int code, int* n_done, bool need_finalize) {
+  s.status = code;
+  s.finalize = need_finalize ? 1 : 0;
+  atomicAdd(n_done, 1);
+}
+
+__device__ inline void lm_reject(LmState& s, const LmParams& P, int* n_done) {
+  s.rejected++;
+  s.radius /= s.nu;
+  s.nu *= 2.0;
+  if (s.radius < P.min_radius) {
+    lm_finish(s, 5, n_done, true);
+  } else {
+    s.lambda = 1.0 / s.radius;
+  }
+}
+
+// Step-acceptance logic after a sweep evaluated the candidate.  cost_c is the
+// candidate cost, gTd/dDd the full-model terms.  Returns true when the
+// candidate becomes the current point (the caller then flips `par` data).
+__device__ inline bool lm_decide(LmState& s, const LmParams& P, double cost_c, double gTd,
+                                 double dDd, int* n_done) {
+  bool accept = false;
+  s.sweeps++;
+  double* h = s.hist[s.n_hist % kHist];
+  s.n_hist++;
+  h[0] = s.cost;
+  h[1] = cost_c;
+  h[2] = 0.0;
+  h[3] = s.radius;
+  h[4] = 0.0;
+  if (s.first) {
+    s.first = 0;
+    s.cost0 = cost_c;
+    accept = true;
+    if (!isfinite(cost_c)) lm_finish(s, CCG_ERR_NOT_FINITE, n_done, false);
+  } else {
+    const double rnorm = sqrt(2.0 * s.cost);
+    const double model = 0.5 * (s.lambda * dDd - gTd);
+    // rounding noise of the FP64 cost ~ eps/2 * |measurement| * ||r|| (each residual is a
+    // difference of numbers of size meas_scale): below it the gain ratio is meaningless
+    const double noise = P.noise_factor * 1.1102230246251565e-16 * s.meas_scale * rnorm;
+    const bool tiny = model <= noise || sqrt(dDd) <= P.parameter_tolerance * rnorm;
+    const double rho = (s.cost - cost_c) / model;
+    h[2] = rho;
+    h[4] = rnorm > 0.0 ? sqrt(dDd) / rnorm : 0.0;
+    if (tiny || s.blind > 0) {
+      // below the resolution of the FP64 cost: take the step unless the cost rises; one
+      // more such polishing step follows (the Gauss-Newton step is still accurate there,
+      // only its validation is not), then stop
+      if (isfinite(cost_c) && cost_c <= s.cost * (1.0 + kCostNoise) + 4.0 * noise) {
+        accept = true;
+        s.accepted++;
+      } else {
+        s.rejected++;
+      }
+      s.blind++;
+      if (!accept || s.blind >= kBlindSteps) lm_finish(s, 3, n_done, true);
+    } else if (isfinite(cost_c) && model > 0.0 && rho > P.min_relative_decrease) {
+      accept = true;
+      s.accepted++;
+      const double f = 2.0 * rho - 1.0;
+      s.radius = fmin(P.max_radius, s.radius / fmax(1.0 / 3.0, 1.0 - f * f * f));
+      s.nu = 2.0;
+      s.lambda = 1.0 / s.radius;
+      if (s.cost - cost_c <= P.function_tolerance * s.cost) lm_finish(s, 2, n_done, true);
+    } else {
+      lm_reject(s, P, n_done);
+    }
+  }
+  h[5] = accept ? 1.0 : 0.0;
+  if (accept) {
+    s.par ^= 1;
+    s.cost = cost_c;
+  }
+  if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, n_done, true);
+  return accept;
+}
+
+// --------------------------------------------------------------------------
+// warp-level transposing reduction: every lane holds 32 values a[0..32); on
+// return lane L holds (in a[0]) the sum over all lanes of a[L].  31 shuffles
+// instead of 32 x 5, fixed summation order (deterministic).
+// --------------------------------------------------------------------------
+__device__ __forceinline__ double warp_reduce32(double (&a)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = up ? a[i] : a[i + half];
+      const double keep = up ? a[i + half] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return a[0];
+}
+
+// Reduce N lane-private accumulators; element e ends up in lane (e & 31),
+// returned slot e >> 5.  out[] has (N+31)/32 entries.
+template <int N>
+__device__ __forceinline__ void warp_reduce_array(const double (&acc)[N], int lane,
+                                                  double (&out)[(N + 31) / 32]) {
+#pragma unroll
+  for (int c = 0; c < (N + 31) / 32; ++c) {
+    double tmp[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tmp[i] = (c * 32 + i < N) ? acc[c * 32 + i] : 0.0;
+    out[c] = warp_reduce32(tmp, lane);
+  }
+}
+
+// In-place Cholesky of a 6x6 SPD matrix held in registers (lower triangle).
+__device__ __forceinline__ bool chol6(double (&A)[6][6]) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+    ok = ok && (d > 0.0) && isfinite(d);
+    d = sqrt(d);
+    A[j][j] = d;
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double s = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
+      A[i][j] = s * inv;
+    }
+  }
+  return ok;
+}
+
+__device__ __forceinline__ void chol6_solve(const double (&L)[6][6], double (&b)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i][k] * b[k];
+    b[i] = s / L[i][i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= L[k][i] * b[k];
+    b[i] = s / L[i][i];
+  }
+}
+
+// Dense Cholesky solve for the small reduced system (n <= 96), one thread.
+__device__ inline bool chol_dense(double* A, int n) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[j * n + j];
+    for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    d = sqrt(d);
+    A[j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[i * n + j];
+      for (int k = 0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = s / d;
+    }
+  }
+  return true;
+}
+__device__ inline void chol_dense_solve(const double* L, int n, double* b) {
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= L[i * n + k] * b[k];
+    b[i] = s / L[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * b[k];
+    b[i] = s / L[i * n + i];
+  }
+}
+
+// [ext] ceres::QuaternionManifold::Plus: x_plus = exp_q(delta) * x, delta = half
+// rotation vector (reference selects it at calibrator.cpp:298,
+// extrinsics_calibrator.cpp:186,196).
+__device__ __forceinline__ void quat_plus(const double (&x)[4], double d0, double d1, double d2,
+                                          double (&out)[4]) {
+  const double n2 = d0 * d0 + d1 * d1 + d2 * d2;
+  double qw, s;
+  if (n2 > 0.0) {
+    const double n = sqrt(n2);
+    double sn, cs;
+    sincos(n, &sn, &cs);
+    qw = cs;
+    s = sn / n;
+  } else {
+    qw = 1.0;
+    s = 1.0;
+  }
+  const double qa = s * d0, qb = s * d1, qc = s * d2;
+  out[0] = qw * x[0] - qa * x[1] - qb * x[2] - qc * x[3];
+  out[1] = qw * x[1] + qa * x[0] + qb * x[3] - qc * x[2];
+  out[2] = qw * x[2] - qa * x[3] + qb * x[0] + qc * x[1];
+  out[3] = qw * x[3] + qa * x[2] - qb * x[1] + qc * x[0];
+}
+
+// rotation matrix (row-major) of q/|q|
+__device__ __forceinline__ void quat_to_rot(const double (&q)[4], double (&R)[9]) {
+  const double inv = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double w = q[0] * inv, a = q[1] * inv, b = q[2] * inv, c = q[3] * inv;
+  R[0] = 1.0 - 2.0 * (b * b + c * c);
+  R[1] = 2.0 * (a * b - w * c);
+  R[2] = 2.0 * (a * c + w * b);
+  R[3] = 2.0 * (a * b + w * c);
+  R[4] = 1.0 - 2.0 * (a * a + c * c);
+  R[5] = 2.0 * (b * c - w * a);
+  R[6] = 2.0 * (a * c - w * b);
+  R[7] = 2.0 * (b * c + w * a);
+  R[8] = 1.0 - 2.0 * (a * a + b * b);
+}
+
+#endif  // __CUDACC__
+
+// --------------------------------------------------------------------------
+// host utilities
+// --------------------------------------------------------------------------
+// Event-pair profiler for opts.profile: tags kernel classes, sums elapsed time
+// per tag after the loop (events are recorded on the library's own stream).
+struct Profiler {
+  ccg_ctx* ctx = nullptr;
+  bool on = false;
+  struct Rec {
+    int tag;
+    size_t e0, e1;
+  };
+  std::vector<Rec> recs;
+  size_t used = 0;
+  size_t grab();
+  void begin(int tag);
+  void end();
+  void collect(double out_ms[4], int out_n[4]);
+};
+
+// split `n_views` views of each problem into work items of at most
+// `views_per_item` consecutive views; returns items as (problem, v0, v1, 0)
+struct WorkItem {
+  int problem, v0, v1, pad;
+};
+
+}  // namespace ccg

@@ -1,0 +1,317 @@
+// Context, error reporting, NCCL plumbing (dlopen, no link-time dependency),
+// event profiler and the peak micro-benchmarks of the ccg library.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace ccg {
+
+int set_error(ccg_ctx* ctx, int status, const char* what, cudaError_t e) {
+  if (ctx) {
+    ctx->last_error = what ? what : "";
+    if (e != cudaSuccess) {
+      ctx->last_error += ": ";
+      ctx->last_error += cudaGetErrorString(e);
+    }
+  }
+  return status;
+}
+
+// ---------------------------------------------------------------- NCCL ----
+// Only ncclAllReduce(sum, double) on a few hundred bytes per LM iteration is
+// needed.  The entry points are resolved at run time from whichever
+// libnccl.so.2 the process already has (torch's bundled one) or can find.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool load_nccl() {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // already in the process (torch)?
+    if (h) break;
+  }
+  if (!h)
+    for (const char* n : names) {
+      h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+  if (!h) return false;
+  g_nccl.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) return false;
+  g_nccl.lib = h;
+  return true;
+}
+
+int nccl_allreduce_sum(ccg_ctx* ctx, double* buf, size_t count) {
+  if (!ctx->nccl_comm) return set_error(ctx, CCG_ERR_NCCL, "no communicator");
+  // ncclFloat64 = 8, ncclSum = 0 (stable enum values of nccl.h)
+  const int rc = g_nccl.AllReduce(buf, buf, count, 8, 0, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return set_error(ctx, CCG_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllReduce");
+  return CCG_OK;
+}
+
+// ------------------------------------------------------------ profiler ----
+size_t Profiler::grab() {
+  if (used == ctx->events.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->events.push_back(e);
+  }
+  return used++;
+}
+void Profiler::begin(int tag) {
+  if (!on) return;
+  Rec r;
+  r.tag = tag;
+  r.e0 = grab();
+  r.e1 = grab();
+  cudaEventRecord(ctx->events[r.e0], ctx->stream);
+  recs.push_back(r);
+}
+void Profiler::end() {
+  if (!on) return;
+  cudaEventRecord(ctx->events[recs.back().e1], ctx->stream);
+}
+void Profiler::collect(double out_ms[4], int out_n[4]) {
+  for (int i = 0; i < 4; ++i) {
+    out_ms[i] = 0.0;
+    out_n[i] = 0;
+  }
+  if (!on) return;
+  for (const Rec& r : recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->events[r.e0], ctx->events[r.e1]);
+    out_ms[r.tag] += ms;
+    out_n[r.tag] += 1;
+  }
+}
+
+// ------------------------------------------------- peak micro-benchmarks ----
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      x0 = fma(x0, a, b);
+      x1 = fma(x1, a, b);
+      x2 = fma(x2, a, b);
+      x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b);
+      x5 = fma(x5, a, b);
+      x6 = fma(x6, a, b);
+      x7 = fma(x7, a, b);
+    }
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) out[0] = s;  // keep the chain alive
+}
+
+__global__ void __launch_bounds__(256) k_copy(const double2* __restrict__ src, double2* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+}  // namespace ccg
+
+using namespace ccg;
+
+extern "C" {
+
+void ccg_default_opts(ccg_opts* o) {
+  o->max_iterations = 100;
+  o->profile = 0;
+  o->initial_radius = 1e4;
+  o->max_radius = 1e16;
+  o->min_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_diagonal = 1e-6;
+  o->max_diagonal = 1e32;
+  o->function_tolerance = 1e-16;
+  o->gradient_tolerance = 1e-12;
+  o->parameter_tolerance = 1e-9;
+  o->noise_factor = 4.0;
+  o->huber_a = (double)(3.0f / 500.0f);
+}
+
+const char* ccg_status_string(int status) {
+  switch (status) {
+    case CCG_OK: return "ok";
+    case CCG_ERR_BAD_ARG: return "bad argument";
+    case CCG_ERR_CUDA: return "CUDA error (no usable device, or a runtime call failed)";
+    case CCG_ERR_NOT_FINITE: return "initial cost is not finite";
+    case CCG_ERR_NCCL: return "NCCL error";
+    case CCG_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+
+const char* ccg_last_error(const ccg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int ccg_init(int device, ccg_ctx** out) {
+  if (!out) return CCG_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return CCG_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return CCG_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CCG_ERR_CUDA;
+  ccg_ctx* c = new ccg_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  c->global_mem = prop.totalGlobalMem;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&c->h_poll, 64) != cudaSuccess) {
+    delete c;
+    return CCG_ERR_CUDA;
+  }
+  *out = c;
+  return CCG_OK;
+}
+
+void ccg_destroy(ccg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+  for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+  if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int ccg_device_info(ccg_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
+                    int64_t* global_mem_bytes) {
+  if (!ctx) return CCG_ERR_BAD_ARG;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (global_mem_bytes) *global_mem_bytes = (int64_t)ctx->global_mem;
+  return CCG_OK;
+}
+
+int ccg_comm_unique_id(uint8_t id_out[128]) {
+  if (!load_nccl()) return CCG_ERR_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return CCG_ERR_NCCL;
+  std::memcpy(id_out, id.internal, 128);
+  return CCG_OK;
+}
+
+int ccg_comm_init(ccg_ctx* ctx, int rank, int world_size, const uint8_t id[128]) {
+  if (!ctx || rank < 0 || world_size < 1 || rank >= world_size) return CCG_ERR_BAD_ARG;
+  ctx->rank = rank;
+  ctx->world = world_size;
+  if (world_size == 1) return CCG_OK;
+  if (!load_nccl()) return set_error(ctx, CCG_ERR_NCCL, "libnccl.so.2 not found");
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  ncclUniqueId uid;
+  std::memcpy(uid.internal, id, 128);
+  ncclComm_t comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, world_size, uid, rank);
+  if (rc != 0) return set_error(ctx, CCG_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitRank");
+  ctx->nccl_comm = comm;
+  return CCG_OK;
+}
+
+int ccg_comm_barrier(ccg_ctx* ctx) {
+  if (!ctx) return CCG_ERR_BAD_ARG;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->world > 1) {
+    double* d = nullptr;
+    CCG_CUDA(ctx, cudaMalloc(&d, sizeof(double)));
+    CCG_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(double), ctx->stream));
+    const int rc = nccl_allreduce_sum(ctx, d, 1);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (rc != CCG_OK) return rc;
+  }
+  CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CCG_OK;
+}
+
+int ccg_measure_fp64_peak(ccg_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return CCG_ERR_BAD_ARG;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* d = nullptr;
+  CCG_CUDA(ctx, cudaMalloc(&d, 8));
+  const int iters = 4096, blocks = ctx->sm_count * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    k_dfma_peak<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1.0000001, 1e-9);
+    ctx->launches++;
+    cudaEventRecord(e1, ctx->stream);
+    CCG_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return CCG_OK;
+}
+
+int ccg_measure_copy_bandwidth(ccg_ctx* ctx, int64_t bytes, double* gbps) {
+  if (!ctx || !gbps || bytes < 16) return CCG_ERR_BAD_ARG;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)bytes / sizeof(double2);
+  double2 *a = nullptr, *b = nullptr;
+  CCG_CUDA(ctx, cudaMalloc(&a, n * sizeof(double2)));
+  if (cudaMalloc(&b, n * sizeof(double2)) != cudaSuccess) {
+    cudaFree(a);
+    return set_error(ctx, CCG_ERR_CUDA, "cudaMalloc");
+  }
+  cudaMemsetAsync(a, 1, n * sizeof(double2), ctx->stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    k_copy<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, b, n);
+    ctx->launches++;
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double g = 2.0 * (double)(n * sizeof(double2)) / (ms * 1e-3) / 1e9;
+    if (rep > 0 && g > best) best = g;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(a);
+  cudaFree(b);
+  *gbps = best;
+  return CCG_OK;
+}
+
+int64_t ccg_kernel_launches(const ccg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

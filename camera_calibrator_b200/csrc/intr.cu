@@ -1,0 +1,1111 @@
+// Single-camera hot path: residual + analytic Jacobian + normal-equation
+// blocks + Schur elimination of the per-view poses + device-resident LM loop.
+//
+// Replaces, behind ccg_intrinsics_*:
+//   the per-observation autodiff evaluation of ReprojectionError
+//       reference src/calibrator.cpp:183-219 (model :70-95, layout :168-179)
+//   the Ceres problem build and ceres::Solve call
+//       reference src/calibrator.cpp:236-324
+// Design (DESIGN.md "Single-camera kernels"):
+//   * observations live in HBM as SoA float32 (u,v,X,Y,Z: 20 B/obs), read with
+//     coalesced 128-byte warp loads; pose and intrinsics are staged per view
+//   * a warp PAIR owns a view: both warps sweep all of its observations, warp A
+//     accumulates V(21) g_v(6) W[:,fx fy px py](24) + cost, warp B accumulates
+//     W[:,k1 k2 p1 p2 k3](30) + U(35) + g_u(9).  Lane-private FP64 accumulators,
+//     one transposing shuffle reduction per view (31 shuffles per 32 values)
+//   * the 9x9 reduced system is summed from per-CTA partials in a fixed order,
+//     so results are bit-reproducible for a given launch geometry
+//   * accept/reject, trust-region update and termination run on the device;
+//     the host only enqueues kernels and polls one counter
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ccg {
+
+constexpr int kBlk = 84;        // per-view block stride (doubles): V21 | gv6 | W4 24 | W5 30 | pad 3
+constexpr int kYz = 72;         // per-view elimination record: Y 54 | z 6 | gv 6 | Dv 6
+constexpr int kPose = 8;        // q4 t3 pad
+constexpr int kSweepPart = 64;  // per-item sweep partial (doubles)
+constexpr int kSchurPart = 96;  // per-item elimination partial
+constexpr int kWarps = 8;       // warps per CTA (4 view pairs in the sweep, 8 views in the elimination)
+
+// sweep partial layout
+//  [0] sum r^2   [1] U fxfx [2] U fxpx [3] U pxpx(=n) [4] U fyfy [5] U fypy [6] U pypy
+//  [7] g'd (poses) [8] d'Dd (poses)                                   <- warp A, slots 0..15
+//  [16..24] g_u (fx fy px py k1 k2 p1 p2 k3)
+//  [25..29] U fx,d  [30..34] U px,d  [35..39] U fy,d  [40..44] U py,d  [45..59] U d,d (packed upper)
+//                                                                      <- warp B, slots 16..63
+
+struct IntrState {
+  LmState lm;
+  double intr[2][9];
+  double du[9];
+  double U[81];  // at the current point, full symmetric
+  double gu[9];
+  int item0, item1;
+  unsigned mask;
+  int pad_;
+};
+
+struct IntrDev {
+  const float *u, *v, *X, *Y, *Z;
+  const int64_t* view_off;
+  const WorkItem* items;
+  double* pose[2];
+  double* blk[2];
+  double* yz;
+  double* sweep_part;
+  double* schur_part;
+  double* red_sweep;  // [B][64]
+  double* red_schur;  // [B][96]
+  IntrState* ps;
+  int* n_done;
+  int64_t obs_base;   // view_off[0]
+};
+
+// --------------------------------------------------------------------------
+// per-observation geometry shared by both warps of a pair
+// --------------------------------------------------------------------------
+struct ObsGeom {
+  double xn, yn, r2, r4, r6, a1, a2, a3, xd, yd;
+  double ju[6], jv[6];
+};
+
+__device__ __forceinline__ void obs_geometry(const double (&R)[9], const double (&t)[3],
+                                             const double (&k)[9], float Xf, float Yf, float Zf,
+                                             ObsGeom& g) {
+  const double X = (double)Xf, Y = (double)Yf, Z = (double)Zf;
+  // rotated point (before translation) and camera-frame point
+  const double y0 = R[0] * X + R[1] * Y + R[2] * Z;
+  const double y1 = R[3] * X + R[4] * Y + R[5] * Z;
+  const double y2 = R[6] * X + R[7] * Y + R[8] * Z;
+  const double iz = 1.0 / (y2 + t[2]);
+  const double xn = (y0 + t[0]) * iz, yn = (y1 + t[1]) * iz;
+  const double fx = k[0], fy = k[1], k1 = k[4], k2 = k[5], p1 = k[6], p2 = k[7], k3 = k[8];
+  const double r2 = xn * xn + yn * yn, r4 = r2 * r2, r6 = r4 * r2;
+  const double m = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+  const double a1 = 2.0 * xn * yn, a2 = r2 + 2.0 * xn * xn, a3 = r2 + 2.0 * yn * yn;
+  g.xn = xn; g.yn = yn; g.r2 = r2; g.r4 = r4; g.r6 = r6; g.a1 = a1; g.a2 = a2; g.a3 = a3;
+  g.xd = xn * m + p1 * a1 + p2 * a2;
+  g.yd = yn * m + p2 * a1 + p1 * a3;
+  // d(xd,yd)/d(xn,yn) (symmetric off-diagonal)
+  const double mp = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
+  const double F00 = m + 2.0 * xn * xn * mp + 2.0 * p1 * yn + 6.0 * p2 * xn;
+  const double F01 = a1 * mp + 2.0 * p1 * xn + 2.0 * p2 * yn;
+  const double F11 = m + 2.0 * yn * yn * mp + 2.0 * p2 * xn + 6.0 * p1 * yn;
+  // d(xn,yn)/d(pose tangent): rotation part uses d y/d delta = -2 [y]x (half-angle tangent)
+  const double A0 = fx * iz * F00, A1 = fx * iz * F01, B0 = fy * iz * F01, B1 = fy * iz * F11;
+  const double c00 = -2.0 * xn * y1, c01 = 2.0 * (y2 + xn * y0), c02 = -2.0 * y1;
+  const double c10 = -2.0 * (y2 + yn * y1), c11 = 2.0 * yn * y0, c12 = 2.0 * y0;
+  g.ju[0] = A0 * c00 + A1 * c10;
+  g.ju[1] = A0 * c01 + A1 * c11;
+  g.ju[2] = A0 * c02 + A1 * c12;
+  g.ju[3] = A0;
+  g.ju[4] = A1;
+  g.ju[5] = -(A0 * xn + A1 * yn);
+  g.jv[0] = B0 * c00 + B1 * c10;
+  g.jv[1] = B0 * c01 + B1 * c11;
+  g.jv[2] = B0 * c02 + B1 * c12;
+  g.jv[3] = B0;
+  g.jv[4] = B1;
+  g.jv[5] = -(B0 * xn + B1 * yn);
+}
+
+// Candidate pose of a view: current pose (+) delta_v, delta_v = -z - Y du.
+// Returns R, t of the candidate; lanes 0..5 of warp A also return their share
+// of g'd and d'Dd; warp A stores the candidate pose.
+__device__ __forceinline__ void view_prologue(const IntrDev& d, int par, int64_t v, int lane,
+                                              bool is_a, const double* s_du, double (&R)[9],
+                                              double (&t)[3], double& gTd, double& dDd) {
+  const double* yz = d.yz + (size_t)v * kYz;
+  double dl = 0.0;
+  if (lane < 6) {
+    dl = -yz[54 + lane];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) dl -= yz[lane * 9 + j] * s_du[j];
+    if (is_a) {
+      gTd += yz[60 + lane] * dl;
+      dDd += dl * dl * yz[66 + lane];
+    }
+  }
+  const double d0 = __shfl_sync(0xffffffffu, dl, 0), d1 = __shfl_sync(0xffffffffu, dl, 1),
+               d2 = __shfl_sync(0xffffffffu, dl, 2), d3 = __shfl_sync(0xffffffffu, dl, 3),
+               d4 = __shfl_sync(0xffffffffu, dl, 4), d5 = __shfl_sync(0xffffffffu, dl, 5);
+  const double* pc = d.pose[par] + (size_t)v * kPose;
+  double q[4] = {pc[0], pc[1], pc[2], pc[3]};
+  double qn[4];
+  quat_plus(q, d0, d1, d2, qn);
+  t[0] = pc[4] + d3;
+  t[1] = pc[5] + d4;
+  t[2] = pc[6] + d5;
+  if (is_a && lane < 7) {
+    double* pn = d.pose[par ^ 1] + (size_t)v * kPose;
+    const double val = lane == 0 ? qn[0] : lane == 1 ? qn[1] : lane == 2 ? qn[2] : lane == 3 ? qn[3]
+                     : lane == 4 ? t[0] : lane == 5 ? t[1] : t[2];
+    pn[lane] = val;
+  }
+  quat_to_rot(qn, R);
+}
+
+// --------------------------------------------------------------------------
+// sweep: residual + Jacobian + normal-equation blocks at the candidate point
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep(IntrDev d, double* __restrict__ res_out) {
+  __shared__ double s_part[kWarps][kSweepPart];
+  __shared__ double s_k[9], s_du[9];
+  __shared__ int s_meta[2];
+  const WorkItem it = d.items[blockIdx.x];
+  IntrState& ps = d.ps[it.problem];
+  if (threadIdx.x == 0) {
+    s_meta[0] = ps.lm.par;
+    s_meta[1] = (ps.lm.status == 0 && ps.lm.solve_ok) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_meta[1]) return;
+  const int par = s_meta[0];
+  if (threadIdx.x < 9) {
+    s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
+    s_du[threadIdx.x] = ps.du[threadIdx.x];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1;
+  const bool is_a = (warp & 1) == 0;
+  double k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = s_k[i];
+
+  if (is_a) {
+    // ---------------- warp A: V, g_v, W[:,0..3], cost, U(fx,px,fy,py block)
+    double pa[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) pa[i] = 0.0;
+    for (int64_t v = it.v0 + pair; v < it.v1; v += kWarps / 2) {
+      double R[9], t[3];
+      view_prologue(d, par, v, lane, true, s_du, R, t, pa[7], pa[8]);
+      double acc[51];
+#pragma unroll
+      for (int i = 0; i < 51; ++i) acc[i] = 0.0;
+      const int64_t o1 = d.view_off[v + 1];
+      for (int64_t o = d.view_off[v] + lane; o < o1; o += 32) {
+        const float mu = __ldg(d.u + o), mv = __ldg(d.v + o);
+        ObsGeom g;
+        obs_geometry(R, t, k, __ldg(d.X + o), __ldg(d.Y + o), __ldg(d.Z + o), g);
+        const double ru = k[0] * g.xd + k[2] - (double)mu;
+        const double rv = k[1] * g.yd + k[3] - (double)mv;
+        if (res_out) {
+          res_out[2 * (o - d.obs_base)] = ru;
+          res_out[2 * (o - d.obs_base) + 1] = rv;
+        }
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = a; b < 6; ++b) {
+            acc[idx] = fma(g.ju[a], g.ju[b], fma(g.jv[a], g.jv[b], acc[idx]));
+            ++idx;
+          }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          acc[21 + a] = fma(g.ju[a], ru, fma(g.jv[a], rv, acc[21 + a]));
+          acc[27 + a * 4 + 0] = fma(g.ju[a], g.xd, acc[27 + a * 4 + 0]);
+          acc[27 + a * 4 + 1] = fma(g.jv[a], g.yd, acc[27 + a * 4 + 1]);
+          acc[27 + a * 4 + 2] += g.ju[a];
+          acc[27 + a * 4 + 3] += g.jv[a];
+        }
+        pa[0] = fma(ru, ru, fma(rv, rv, pa[0]));
+        pa[1] = fma(g.xd, g.xd, pa[1]);
+        pa[2] += g.xd;
+        pa[3] += 1.0;
+        pa[4] = fma(g.yd, g.yd, pa[4]);
+        pa[5] += g.yd;
+        pa[6] += 1.0;
+      }
+      double out[2];
+      warp_reduce_array<51>(acc, lane, out);
+      double* blk = d.blk[par ^ 1] + (size_t)v * kBlk;
+      blk[lane] = out[0];
+      if (lane < 51 - 32) blk[32 + lane] = out[1];
+    }
+    // g'd and d'Dd are spread over lanes 0..5; the transposing reduction sums each slot over all lanes
+    double out[1];
+    warp_reduce_array<9>(pa, lane, out);
+    if (lane < 16) s_part[warp][lane] = lane < 9 ? out[0] : 0.0;
+  } else {
+    // ---------------- warp B: W[:,4..8], g_u, U (everything involving distortion)
+    double pb[44];
+#pragma unroll
+    for (int i = 0; i < 44; ++i) pb[i] = 0.0;
+    for (int64_t v = it.v0 + pair; v < it.v1; v += kWarps / 2) {
+      double R[9], t[3], dum0 = 0.0, dum1 = 0.0;
+      view_prologue(d, par, v, lane, false, s_du, R, t, dum0, dum1);
+      double acc[30];
+#pragma unroll
+      for (int i = 0; i < 30; ++i) acc[i] = 0.0;
+      const int64_t o1 = d.view_off[v + 1];
+      for (int64_t o = d.view_off[v] + lane; o < o1; o += 32) {
+        const float mu = __ldg(d.u + o), mv = __ldg(d.v + o);
+        ObsGeom g;
+        obs_geometry(R, t, k, __ldg(d.X + o), __ldg(d.Y + o), __ldg(d.Z + o), g);
+        const double ru = k[0] * g.xd + k[2] - (double)mu;
+        const double rv = k[1] * g.yd + k[3] - (double)mv;
+        double au[5], av[5];
+        au[0] = k[0] * g.xn * g.r2; au[1] = k[0] * g.xn * g.r4; au[2] = k[0] * g.a1;
+        au[3] = k[0] * g.a2;        au[4] = k[0] * g.xn * g.r6;
+        av[0] = k[1] * g.yn * g.r2; av[1] = k[1] * g.yn * g.r4; av[2] = k[1] * g.a3;
+        av[3] = k[1] * g.a1;        av[4] = k[1] * g.yn * g.r6;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = 0; c < 5; ++c)
+            acc[a * 5 + c] = fma(g.ju[a], au[c], fma(g.jv[a], av[c], acc[a * 5 + c]));
+        pb[0] = fma(g.xd, ru, pb[0]);
+        pb[1] = fma(g.yd, rv, pb[1]);
+        pb[2] += ru;
+        pb[3] += rv;
+        int idx = 29;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          pb[4 + c] = fma(au[c], ru, fma(av[c], rv, pb[4 + c]));
+          pb[9 + c] = fma(g.xd, au[c], pb[9 + c]);
+          pb[14 + c] += au[c];
+          pb[19 + c] = fma(g.yd, av[c], pb[19 + c]);
+          pb[24 + c] += av[c];
+#pragma unroll
+          for (int e = c; e < 5; ++e) {
+            pb[idx] = fma(au[c], au[e], fma(av[c], av[e], pb[idx]));
+            ++idx;
+          }
+        }
+      }
+      double out[1];
+      warp_reduce_array<30>(acc, lane, out);
+      if (lane < 30) d.blk[par ^ 1][(size_t)v * kBlk + 51 + lane] = out[0];
+    }
+    double out[2];
+    warp_reduce_array<44>(pb, lane, out);
+    s_part[warp][16 + lane] = out[0];
+    if (lane < 16) s_part[warp][48 + lane] = lane < 12 ? out[1] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < kSweepPart) {
+    const int c = threadIdx.x;
+    const int w0 = c < 16 ? 0 : 1;  // slots 0..15 come from A warps, the rest from B warps
+    double s = 0.0;
+#pragma unroll
+    for (int p = 0; p < kWarps / 2; ++p) s += s_part[2 * p + w0][c];
+    d.sweep_part[(size_t)blockIdx.x * kSweepPart + c] = s;
+  }
+}
+
+// --------------------------------------------------------------------------
+// pose elimination: per view Cholesky of V + lambda D, Y = V'^-1 W, z = V'^-1 g_v,
+// contributions W'Y and W'z to the reduced system
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32) k_intr_schur(IntrDev d, LmParams P) {
+  __shared__ double s_part[kWarps][kSchurPart];
+  __shared__ int s_meta[2];
+  __shared__ double s_lambda;
+  const WorkItem it = d.items[blockIdx.x];
+  IntrState& ps = d.ps[it.problem];
+  if (threadIdx.x == 0) {
+    s_meta[0] = ps.lm.par;
+    s_meta[1] = (ps.lm.status == 0 || ps.lm.finalize) ? 1 : 0;
+    s_lambda = ps.lm.lambda;
+  }
+  __syncthreads();
+  if (!s_meta[1]) return;
+  const int par = s_meta[0];
+  const double lambda = s_lambda;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double acc[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = 0.0;
+  double gDg = 0.0, fails = 0.0;
+  for (int64_t v = it.v0 + warp; v < it.v1; v += kWarps) {
+    const double* blk = d.blk[par] + (size_t)v * kBlk;
+    double A[6][6], Dv[6], gv[6];
+    {
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) {
+          A[b][a] = blk[idx];
+          ++idx;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      gv[a] = blk[21 + a];
+      Dv[a] = clampd(A[a][a], P.min_diagonal, P.max_diagonal);
+      if (lane == 0 && A[a][a] > 0.0) gDg += gv[a] * gv[a] / A[a][a];
+      A[a][a] += lambda * Dv[a];
+    }
+    const bool ok = chol6(A);
+    if (!ok && lane == 0) fails += 1.0;
+    // column `lane` of [W | g_v]
+    double col[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double w = 0.0;
+      if (lane < 4) w = blk[27 + a * 4 + lane];
+      else if (lane < 9) w = blk[51 + a * 5 + (lane - 4)];
+      else if (lane == 9) w = gv[a];
+      col[a] = w;
+    }
+    double y[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) y[a] = col[a];
+    chol6_solve(A, y);
+    double* yz = d.yz + (size_t)v * kYz;
+    if (lane < 9) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) yz[a * 9 + lane] = y[a];
+    } else if (lane == 9) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) yz[54 + a] = y[a];
+    } else if (lane == 10) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) yz[60 + a] = gv[a];
+    } else if (lane == 11) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) yz[66 + a] = Dv[a];
+    }
+    // acc[j] (lane k) += W[:,j] . y_k   ->  (W'Y)[j][k] for k < 9, (W'z)[j] for k == 9
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s = fma(__shfl_sync(0xffffffffu, col[a], j), y[a], s);
+      acc[j] += s;
+    }
+  }
+  if (lane < 10) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) s_part[warp][lane * 9 + j] = acc[j];
+  }
+  if (lane == 0) {
+    s_part[warp][90] = gDg;
+    s_part[warp][91] = fails;
+  }
+  __syncthreads();
+  if (threadIdx.x < kSchurPart) {
+    double s = 0.0;
+    if (threadIdx.x < 92) {
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += s_part[w][threadIdx.x];
+    }
+    d.schur_part[(size_t)blockIdx.x * kSchurPart + threadIdx.x] = s;
+  }
+}
+
+// --------------------------------------------------------------------------
+// fixed-order reduction of per-item partials of one problem (blockIdx.x)
+// --------------------------------------------------------------------------
+constexpr int kRedSeg = 8;
+template <int STRIDE>
+__device__ __forceinline__ void block_reduce_items(const double* part, int item0, int item1,
+                                                   double* s_buf /* [kRedSeg][STRIDE] */) {
+  const int c = threadIdx.x % STRIDE, seg = threadIdx.x / STRIDE;
+  double s = 0.0;
+  for (int i = item0 + seg; i < item1; i += kRedSeg) s += part[(size_t)i * STRIDE + c];
+  s_buf[seg * STRIDE + c] = s;
+  __syncthreads();
+  if (seg == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int g = 0; g < kRedSeg; ++g) tot += s_buf[g * STRIDE + c];
+    s_buf[c] = tot;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_reduce_sweep(IntrDev d) {
+  __shared__ double s_buf[kRedSeg * kSweepPart];
+  IntrState& ps = d.ps[blockIdx.x];
+  if (!(ps.lm.status == 0 && ps.lm.solve_ok)) return;
+  block_reduce_items<kSweepPart>(d.sweep_part, ps.item0, ps.item1, s_buf);
+  if (threadIdx.x < kSweepPart) d.red_sweep[(size_t)blockIdx.x * kSweepPart + threadIdx.x] = s_buf[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_reduce_schur(IntrDev d) {
+  __shared__ double s_buf[kRedSeg * kSchurPart];
+  IntrState& ps = d.ps[blockIdx.x];
+  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
+  block_reduce_items<kSchurPart>(d.schur_part, ps.item0, ps.item1, s_buf);
+  if (threadIdx.x < kSchurPart) d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x] = s_buf[threadIdx.x];
+}
+
+// unpack the reduced sweep partial into the full symmetric 9x9 U and g_u
+__device__ inline void unpack_U(const double* r, double* U, double* gu) {
+  for (int i = 0; i < 81; ++i) U[i] = 0.0;
+  auto set = [&](int a, int b, double v) { U[a * 9 + b] = v; U[b * 9 + a] = v; };
+  set(0, 0, r[1]); set(0, 2, r[2]); set(2, 2, r[3]);
+  set(1, 1, r[4]); set(1, 3, r[5]); set(3, 3, r[6]);
+  int idx = 45;
+  for (int c = 0; c < 5; ++c) {
+    set(0, 4 + c, r[25 + c]);
+    set(2, 4 + c, r[30 + c]);
+    set(1, 4 + c, r[35 + c]);
+    set(3, 4 + c, r[40 + c]);
+    for (int e = c; e < 5; ++e) set(4 + c, 4 + e, r[idx++]);
+  }
+  for (int i = 0; i < 9; ++i) gu[i] = r[16 + i];
+}
+
+// accept / reject after a sweep.  REDUCE: sum the partials here (single GPU);
+// otherwise read the (all-reduced) red_sweep buffer.
+template <bool REDUCE>
+__global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_decide(IntrDev d, LmParams P) {
+  __shared__ double s_buf[kRedSeg * kSweepPart];
+  IntrState& ps = d.ps[blockIdx.x];
+  if (ps.lm.status != 0) return;
+  const bool evaluated = ps.lm.solve_ok != 0;
+  if (evaluated) {
+    if (REDUCE) {
+      block_reduce_items<kSweepPart>(d.sweep_part, ps.item0, ps.item1, s_buf);
+    } else {
+      if (threadIdx.x < kSweepPart) s_buf[threadIdx.x] = d.red_sweep[(size_t)blockIdx.x * kSweepPart + threadIdx.x];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x != 0) return;
+  LmState& s = ps.lm;
+  if (!evaluated) {
+    // the linear solve failed (non-PD): shrink the trust region and retry
+    lm_reject(s, P, d.n_done);
+    s.solve_ok = 1;
+    if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, d.n_done, true);
+    return;
+  }
+  const double* r = s_buf;
+  const double cost_c = 0.5 * r[0];
+  const bool accept = lm_decide(s, P, cost_c, r[7] + s.gTd_u, r[8] + s.dDd_u, d.n_done);
+  if (accept) {
+    unpack_U(r, ps.U, ps.gu);
+    s.n_obs = r[3];
+    s.sumsq = r[0];
+  }
+}
+
+// reduced 9x9 solve.  Also evaluates the gradient norm at the current point.
+template <bool REDUCE>
+__global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, LmParams P) {
+  __shared__ double s_buf[kRedSeg * kSchurPart];
+  IntrState& ps = d.ps[blockIdx.x];
+  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
+  if (REDUCE) {
+    block_reduce_items<kSchurPart>(d.schur_part, ps.item0, ps.item1, s_buf);
+  } else {
+    if (threadIdx.x < kSchurPart) s_buf[threadIdx.x] = d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  LmState& s = ps.lm;
+  const double* r = s_buf;
+  const unsigned mask = ps.mask;
+  const int par = s.par;
+  double gDg = r[90];
+  for (int k = 0; k < 9; ++k)
+    if (!((mask >> k) & 1u) && ps.U[k * 9 + k] > 0.0) gDg += ps.gu[k] * ps.gu[k] / ps.U[k * 9 + k];
+  const double rnorm = sqrt(2.0 * s.cost);
+  s.grad_norm = rnorm > 0.0 ? sqrt(gDg) / rnorm : 0.0;
+  if (s.finalize) {
+    s.finalize = 0;
+    return;
+  }
+  if (s.cost == 0.0 || sqrt(gDg) <= P.gradient_tolerance * rnorm) {
+    lm_finish(s, 1, d.n_done, false);
+    return;
+  }
+  s.iterations++;
+  if (r[91] > 0.0) {
+    s.solve_ok = 0;
+    return;
+  }
+  double S[81], rhs[9], Du[9];
+  const double lambda = s.lambda;
+  for (int a = 0; a < 9; ++a) {
+    Du[a] = clampd(ps.U[a * 9 + a], P.min_diagonal, P.max_diagonal);
+    rhs[a] = -ps.gu[a] + r[81 + a];
+    for (int b = 0; b < 9; ++b) {
+      // (W'Y)[a][b] lives at r[b*9 + a]; symmetrise from the upper triangle
+      const double wy = a <= b ? r[b * 9 + a] : r[a * 9 + b];
+      S[a * 9 + b] = ps.U[a * 9 + b] - wy;
+    }
+    S[a * 9 + a] += lambda * Du[a];
+  }
+  for (int k = 0; k < 9; ++k)
+    if ((mask >> k) & 1u) {
+      for (int b = 0; b < 9; ++b) S[k * 9 + b] = S[b * 9 + k] = 0.0;
+      S[k * 9 + k] = 1.0;
+      rhs[k] = 0.0;
+    }
+  if (!chol_dense(S, 9)) {
+    s.solve_ok = 0;
+    return;
+  }
+  chol_dense_solve(S, 9, rhs);
+  double gTd = 0.0, dDd = 0.0;
+  for (int k = 0; k < 9; ++k) {
+    const double dk = ((mask >> k) & 1u) ? 0.0 : rhs[k];
+    ps.du[k] = dk;
+    ps.intr[par ^ 1][k] = ps.intr[par][k] + dk;
+    gTd += ps.gu[k] * dk;
+    dDd += dk * dk * Du[k];
+  }
+  s.gTd_u = gTd;
+  s.dDd_u = dDd;
+  s.solve_ok = 1;
+}
+
+__global__ void k_intr_init_state(IntrDev d, LmParams P, const double* intr0, const int2* item_ranges,
+                                  const double* meas_scale, unsigned mask, int n_problems) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_problems) return;
+  IntrState& ps = d.ps[b];
+  lm_init(ps.lm, P);
+  ps.lm.meas_scale = meas_scale[b];
+  for (int k = 0; k < 9; ++k) {
+    ps.intr[0][k] = intr0[(size_t)b * 9 + k];
+    ps.intr[1][k] = intr0[(size_t)b * 9 + k];
+    ps.du[k] = 0.0;
+    ps.gu[k] = 0.0;
+  }
+  for (int k = 0; k < 81; ++k) ps.U[k] = 0.0;
+  ps.item0 = item_ranges[b].x;
+  ps.item1 = item_ranges[b].y;
+  ps.mask = mask;
+  ps.pad_ = 0;
+  if (b == 0) *d.n_done = 0;
+}
+
+}  // namespace ccg
+
+// ==========================================================================
+// host side
+// ==========================================================================
+using namespace ccg;
+
+struct ccg_intr_problem {
+  ccg_ctx* ctx = nullptr;
+  int64_t n_views = 0, n_obs = 0, n_problems = 0;
+  int n_items = 0;
+  int shared = 0;
+  unsigned mask = 0;
+  IntrDev dev;
+  // owned device allocations
+  std::vector<void*> allocs;
+  int64_t bytes = 0;
+  double *d_intr0 = nullptr, *d_pose0 = nullptr, *d_meas_scale = nullptr;
+  int2* d_item_ranges = nullptr;
+  float* d_obs = nullptr;
+  std::vector<int64_t> problem_off;  // host copy
+  std::vector<int64_t> problem_obs;  // observations per problem
+  LmParams params;
+  bool params_set = false;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(ccg_intr_problem* p, T** out, size_t n) {
+  void* ptr = nullptr;
+  const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&ptr, bytes);
+  if (e != cudaSuccess) return set_error(p->ctx, CCG_ERR_CUDA, "cudaMalloc", e);
+  p->allocs.push_back(ptr);
+  p->bytes += (int64_t)bytes;
+  *out = (T*)ptr;
+  return CCG_OK;
+}
+
+#define CCG_TRY(x)            \
+  do {                        \
+    const int rc__ = (x);     \
+    if (rc__ != CCG_OK) return rc__; \
+  } while (0)
+
+int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, const float* Y,
+                  const float* Z, const int64_t* view_offsets, int64_t n_views,
+                  const int64_t* problem_offsets, int64_t n_problems, const double* intr,
+                  const double* q, const double* t, unsigned mask, int shared,
+                  ccg_intr_problem* p) {
+  p->ctx = ctx;
+  p->n_views = n_views;
+  p->n_problems = n_problems;
+  p->shared = shared;
+  p->mask = mask;
+  const int64_t o0 = view_offsets[0];
+  const int64_t n_obs = view_offsets[n_views] - o0;
+  p->n_obs = n_obs;
+  cudaStream_t st = ctx->stream;
+
+  // ---- work items: consecutive views of one problem per CTA
+  const int64_t target_items = (int64_t)ctx->sm_count * 4;
+  int64_t vpi = std::max<int64_t>(kWarps / 2, (n_views + target_items - 1) / std::max<int64_t>(target_items, 1));
+  std::vector<WorkItem> items;
+  std::vector<int2> ranges((size_t)n_problems);
+  p->problem_off.assign(problem_offsets, problem_offsets + n_problems + 1);
+  p->problem_obs.resize((size_t)n_problems);
+  for (int64_t b = 0; b < n_problems; ++b) {
+    const int64_t v0 = problem_offsets[b], v1 = problem_offsets[b + 1];
+    if (v1 < v0 || v0 < 0 || v1 > n_views) return set_error(ctx, CCG_ERR_BAD_ARG, "problem_offsets");
+    p->problem_obs[(size_t)b] = view_offsets[v1] - view_offsets[v0];
+    ranges[(size_t)b].x = (int)items.size();
+    const int64_t nv = v1 - v0;
+    const int64_t n_it = std::max<int64_t>(1, (nv + vpi - 1) / vpi);
+    for (int64_t i = 0; i < n_it; ++i) {
+      WorkItem w;
+      w.problem = (int)b;
+      w.v0 = (int)(v0 + nv * i / n_it);
+      w.v1 = (int)(v0 + nv * (i + 1) / n_it);
+      w.pad = 0;
+      items.push_back(w);
+    }
+    ranges[(size_t)b].y = (int)items.size();
+  }
+  p->n_items = (int)items.size();
+
+  // ---- device memory
+  IntrDev& d = p->dev;
+  std::memset(&d, 0, sizeof(d));
+  float* obs = nullptr;
+  CCG_TRY(dev_alloc(p, &obs, (size_t)n_obs * 5));
+  p->d_obs = obs;
+  int64_t* d_voff = nullptr;
+  CCG_TRY(dev_alloc(p, &d_voff, (size_t)n_views + 1));
+  WorkItem* d_items = nullptr;
+  CCG_TRY(dev_alloc(p, &d_items, items.size()));
+  CCG_TRY(dev_alloc(p, &p->d_item_ranges, (size_t)n_problems));
+  CCG_TRY(dev_alloc(p, &d.pose[0], (size_t)n_views * kPose));
+  CCG_TRY(dev_alloc(p, &d.pose[1], (size_t)n_views * kPose));
+  CCG_TRY(dev_alloc(p, &p->d_pose0, (size_t)n_views * kPose));
+  CCG_TRY(dev_alloc(p, &d.blk[0], (size_t)n_views * kBlk));
+  CCG_TRY(dev_alloc(p, &d.blk[1], (size_t)n_views * kBlk));
+  CCG_TRY(dev_alloc(p, &d.yz, (size_t)n_views * kYz));
+  CCG_TRY(dev_alloc(p, &d.sweep_part, items.size() * kSweepPart));
+  CCG_TRY(dev_alloc(p, &d.schur_part, items.size() * kSchurPart));
+  CCG_TRY(dev_alloc(p, &d.red_sweep, (size_t)n_problems * kSweepPart));
+  CCG_TRY(dev_alloc(p, &d.red_schur, (size_t)n_problems * kSchurPart));
+  CCG_TRY(dev_alloc(p, &d.ps, (size_t)n_problems));
+  CCG_TRY(dev_alloc(p, &d.n_done, 1));
+  CCG_TRY(dev_alloc(p, &p->d_intr0, (size_t)n_problems * 9));
+  CCG_TRY(dev_alloc(p, &p->d_meas_scale, (size_t)n_problems));
+
+  // observations are re-based so that view_off[0] == 0 on the device
+  d.u = obs;
+  d.v = obs + n_obs;
+  d.X = obs + 2 * n_obs;
+  d.Y = obs + 3 * n_obs;
+  d.Z = obs + 4 * n_obs;
+  d.view_off = d_voff;
+  d.items = d_items;
+  d.obs_base = 0;
+  CCG_CUDA(ctx, cudaMemcpyAsync(obs, u + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(obs + n_obs, v + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(obs + 2 * n_obs, X + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(obs + 3 * n_obs, Y + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(obs + 4 * n_obs, Z + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
+  std::vector<int64_t> voff((size_t)n_views + 1);
+  for (int64_t i = 0; i <= n_views; ++i) voff[(size_t)i] = view_offsets[i] - o0;
+  std::vector<double> pose((size_t)n_views * kPose, 0.0);
+  for (int64_t i = 0; i < n_views; ++i) {
+    for (int k = 0; k < 4; ++k) pose[(size_t)i * kPose + k] = q[i * 4 + k];
+    for (int k = 0; k < 3; ++k) pose[(size_t)i * kPose + 4 + k] = t[i * 3 + k];
+  }
+  CCG_CUDA(ctx, cudaMemcpyAsync(d_voff, voff.data(), sizeof(int64_t) * voff.size(), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_item_ranges, ranges.data(), sizeof(int2) * ranges.size(), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_pose0, pose.data(), sizeof(double) * pose.size(), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_intr0, intr, sizeof(double) * 9 * n_problems, cudaMemcpyHostToDevice, st));
+  // max |measurement| per problem: the scale of the cost's rounding noise (lm_decide)
+  std::vector<double> mscale((size_t)n_problems, 0.0);
+  for (int64_t b = 0; b < n_problems; ++b) {
+    float m = 0.0f;
+    for (int64_t o = view_offsets[problem_offsets[b]]; o < view_offsets[problem_offsets[b + 1]]; ++o)
+      m = std::max(m, std::max(std::fabs(u[o]), std::fabs(v[o])));
+    mscale[(size_t)b] = (double)m;
+  }
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_meas_scale, mscale.data(), sizeof(double) * n_problems, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaStreamSynchronize(st));  // host staging vectors go out of scope
+  return CCG_OK;
+}
+
+int reset_problem(ccg_intr_problem* p, const LmParams& P) {
+  ccg_ctx* ctx = p->ctx;
+  IntrDev& d = p->dev;
+  cudaStream_t st = ctx->stream;
+  CCG_CUDA(ctx, cudaMemcpyAsync(d.pose[0], p->d_pose0, sizeof(double) * p->n_views * kPose, cudaMemcpyDeviceToDevice, st));
+  CCG_CUDA(ctx, cudaMemsetAsync(d.yz, 0, sizeof(double) * std::max<int64_t>(p->n_views, 1) * kYz, st));
+  const int nb = (int)p->n_problems;
+  k_intr_init_state<<<(nb + 127) / 128, 128, 0, st>>>(d, P, p->d_intr0, p->d_item_ranges, p->d_meas_scale, p->mask, nb);
+  ctx->launches++;
+  CCG_CUDA(ctx, cudaGetLastError());
+  p->params = P;
+  p->params_set = true;
+  return CCG_OK;
+}
+
+enum { TAG_SWEEP = 0, TAG_SCHUR = 1, TAG_SMALL = 2 };
+
+// one residual+Jacobian sweep followed by the accept/reject step
+int launch_sweep_decide(ccg_intr_problem* p, const LmParams& P, Profiler& prof, double* res_out, int* n_allreduce) {
+  ccg_ctx* ctx = p->ctx;
+  IntrDev& d = p->dev;
+  cudaStream_t st = ctx->stream;
+  const int nb = (int)p->n_problems;
+  prof.begin(TAG_SWEEP);
+  k_intr_sweep<<<p->n_items, kWarps * 32, 0, st>>>(d, res_out);
+  prof.end();
+  ctx->launches++;
+  prof.begin(TAG_SMALL);
+  if (p->shared && ctx->world > 1) {
+    k_intr_reduce_sweep<<<nb, kRedSeg * kSweepPart, 0, st>>>(d);
+    CCG_TRY(nccl_allreduce_sum(ctx, d.red_sweep, (size_t)nb * kSweepPart));
+    (*n_allreduce)++;
+    k_intr_decide<false><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P);
+    ctx->launches += 2;
+  } else {
+    k_intr_decide<true><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P);
+    ctx->launches++;
+  }
+  prof.end();
+  return CCG_OK;
+}
+
+int launch_schur_solve(ccg_intr_problem* p, const LmParams& P, Profiler& prof, int* n_allreduce) {
+  ccg_ctx* ctx = p->ctx;
+  IntrDev& d = p->dev;
+  cudaStream_t st = ctx->stream;
+  const int nb = (int)p->n_problems;
+  prof.begin(TAG_SCHUR);
+  k_intr_schur<<<p->n_items, kWarps * 32, 0, st>>>(d, P);
+  prof.end();
+  ctx->launches++;
+  prof.begin(TAG_SMALL);
+  if (p->shared && ctx->world > 1) {
+    k_intr_reduce_schur<<<nb, kRedSeg * kSchurPart, 0, st>>>(d);
+    CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, (size_t)nb * kSchurPart));
+    (*n_allreduce)++;
+    k_intr_solve<false><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P);
+    ctx->launches += 2;
+  } else {
+    k_intr_solve<true><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P);
+    ctx->launches++;
+  }
+  prof.end();
+  return CCG_OK;
+}
+
+int poll_done(ccg_intr_problem* p, int* done) {
+  ccg_ctx* ctx = p->ctx;
+  CCG_CUDA(ctx, cudaMemcpyAsync(ctx->h_poll, p->dev.n_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *done = ctx->h_poll[0];
+  return CCG_OK;
+}
+
+int run_problem(ccg_intr_problem* p, const ccg_opts& opts, ccg_timing* timing) {
+  ccg_ctx* ctx = p->ctx;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const LmParams P = to_params(opts);
+  CCG_TRY(reset_problem(p, P));
+  Profiler prof;
+  prof.ctx = ctx;
+  prof.on = opts.profile != 0;
+  int n_allreduce = 0;
+  size_t ev_total0 = 0, ev_total1 = 0;
+  {
+    // total-loop events are always recorded (cheap)
+    Profiler tot;
+    tot.ctx = ctx;
+    tot.on = true;
+    tot.used = 0;
+    ev_total0 = tot.grab();
+    ev_total1 = tot.grab();
+    prof.used = tot.used;
+  }
+  cudaEventRecord(ctx->events[ev_total0], ctx->stream);
+  CCG_TRY(launch_sweep_decide(p, P, prof, nullptr, &n_allreduce));
+  const int poll_every = 4;
+  int done = 0;
+  for (int it = 0; it <= opts.max_iterations * 2 + 64; ++it) {
+    CCG_TRY(launch_schur_solve(p, P, prof, &n_allreduce));
+    if (done >= (int)p->n_problems) break;  // that was the finalize pass
+    CCG_TRY(launch_sweep_decide(p, P, prof, nullptr, &n_allreduce));
+    if ((it % poll_every) == poll_every - 1) CCG_TRY(poll_done(p, &done));
+  }
+  cudaEventRecord(ctx->events[ev_total1], ctx->stream);
+  CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CCG_CUDA(ctx, cudaGetLastError());
+  if (timing) {
+    std::memset(timing, 0, sizeof(*timing));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->events[ev_total0], ctx->events[ev_total1]);
+    timing->total_ms = ms;
+    double tms[4];
+    int tn[4];
+    prof.collect(tms, tn);
+    timing->sweep_ms = tms[TAG_SWEEP];
+    timing->schur_ms = tms[TAG_SCHUR];
+    timing->small_ms = tms[TAG_SMALL];
+    timing->sweep_launches = tn[TAG_SWEEP];
+    timing->schur_launches = tn[TAG_SCHUR];
+    timing->small_launches = tn[TAG_SMALL];
+    timing->allreduces = n_allreduce;
+    timing->sweep_obs = p->n_obs;
+    timing->sweep_views = p->n_views;
+  }
+  return CCG_OK;
+}
+
+int download_problem(ccg_intr_problem* p, double* intr, double* q, double* t, ccg_report* reports) {
+  ccg_ctx* ctx = p->ctx;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t nb = p->n_problems, nv = p->n_views;
+  std::vector<IntrState> st((size_t)nb);
+  CCG_CUDA(ctx, cudaMemcpyAsync(st.data(), p->dev.ps, sizeof(IntrState) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<double> pose0, pose1;
+  if (q || t) {
+    pose0.resize((size_t)nv * kPose);
+    pose1.resize((size_t)nv * kPose);
+    CCG_CUDA(ctx, cudaMemcpyAsync(pose0.data(), p->dev.pose[0], sizeof(double) * pose0.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CCG_CUDA(ctx, cudaMemcpyAsync(pose1.data(), p->dev.pose[1], sizeof(double) * pose1.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc = CCG_OK;
+  for (int64_t b = 0; b < nb; ++b) {
+    const IntrState& s = st[(size_t)b];
+    const int par = s.lm.par;
+    if (intr)
+      for (int k = 0; k < 9; ++k) intr[b * 9 + k] = s.intr[par][k];
+    if (q || t) {
+      const std::vector<double>& pose = par ? pose1 : pose0;
+      for (int64_t v = p->problem_off[(size_t)b]; v < p->problem_off[(size_t)b + 1]; ++v) {
+        if (q) for (int k = 0; k < 4; ++k) q[v * 4 + k] = pose[(size_t)v * kPose + k];
+        if (t) for (int k = 0; k < 3; ++k) t[v * 3 + k] = pose[(size_t)v * kPose + 4 + k];
+      }
+    }
+    if (reports) {
+      ccg_report& r = reports[b];
+      r.iterations = s.lm.iterations;
+      r.accepted = s.lm.accepted;
+      r.rejected = s.lm.rejected;
+      r.sweeps = s.lm.sweeps;
+      r.termination = s.lm.status;
+      r.pad_ = 0;
+      r.initial_cost = s.lm.cost0;
+      r.final_cost = s.lm.cost;
+      r.gradient_norm = s.lm.grad_norm;
+      r.rms = s.lm.n_obs > 0.0 ? std::sqrt(2.0 * s.lm.cost / s.lm.n_obs) : 0.0;
+    }
+    if (s.lm.status < 0) rc = s.lm.status;
+  }
+  return rc;
+}
+
+void free_problem(ccg_intr_problem* p) {
+  if (!p) return;
+  if (p->ctx) cudaSetDevice(p->ctx->device);
+  for (void* a : p->allocs) cudaFree(a);
+  delete p;
+}
+
+bool bad_inputs(const float* u, const float* v, const float* X, const float* Y, const float* Z,
+                const int64_t* view_offsets, int64_t n_views) {
+  if (!view_offsets || n_views < 0) return true;
+  const int64_t n = view_offsets[n_views] - view_offsets[0];
+  if (n < 0) return true;
+  if (n > 0 && (!u || !v || !X || !Y || !Z)) return true;
+  for (int64_t i = 0; i < n_views; ++i)
+    if (view_offsets[i + 1] < view_offsets[i]) return true;
+  return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccg_intrinsics_create(ccg_ctx* ctx, const float* u, const float* v, const float* X,
+                          const float* Y, const float* Z, const int64_t* view_offsets,
+                          int64_t n_views, const int64_t* problem_offsets, int64_t n_problems,
+                          const double* intr, const double* q, const double* t,
+                          uint32_t const_intr_mask, int shared, ccg_intr_problem** out) {
+  if (!ctx || !out) return CCG_ERR_BAD_ARG;
+  *out = nullptr;
+  if (bad_inputs(u, v, X, Y, Z, view_offsets, n_views) || !intr || n_problems < 1 ||
+      (n_views > 0 && (!q || !t)) || n_views > 0x7fffffff)
+    return set_error(ctx, CCG_ERR_BAD_ARG, "ccg_intrinsics_create: bad argument");
+  if (shared && n_problems != 1) return set_error(ctx, CCG_ERR_UNSUPPORTED, "shared requires n_problems == 1");
+  const int64_t one[2] = {0, n_views};
+  if (!problem_offsets) {
+    if (n_problems != 1) return set_error(ctx, CCG_ERR_BAD_ARG, "problem_offsets required");
+    problem_offsets = one;
+  }
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  ccg_intr_problem* p = new ccg_intr_problem();
+  const int rc = build_problem(ctx, u, v, X, Y, Z, view_offsets, n_views, problem_offsets, n_problems,
+                               intr, q, t, const_intr_mask, shared, p);
+  if (rc != CCG_OK) {
+    free_problem(p);
+    return rc;
+  }
+  *out = p;
+  return CCG_OK;
+}
+
+int ccg_intrinsics_reset(ccg_intr_problem* p) {
+  if (!p) return CCG_ERR_BAD_ARG;
+  ccg_opts o;
+  ccg_default_opts(&o);
+  CCG_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+  return reset_problem(p, p->params_set ? p->params : to_params(o));
+}
+
+int ccg_intrinsics_run(ccg_intr_problem* p, const ccg_opts* opts, ccg_timing* timing) {
+  if (!p) return CCG_ERR_BAD_ARG;
+  ccg_opts o;
+  if (opts) o = *opts; else ccg_default_opts(&o);
+  return run_problem(p, o, timing);
+}
+
+int ccg_intrinsics_time_sweep(ccg_intr_problem* p, int n, float* ms_per_launch) {
+  if (!p || n < 1 || !ms_per_launch) return CCG_ERR_BAD_ARG;
+  ccg_ctx* ctx = p->ctx;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  ccg_opts o;
+  ccg_default_opts(&o);
+  const LmParams P = p->params_set ? p->params : to_params(o);
+  CCG_TRY(reset_problem(p, P));  // status 0, first = 1: every launch evaluates the initial point
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_intr_sweep<<<p->n_items, kWarps * 32, 0, ctx->stream>>>(p->dev, nullptr);  // warm-up
+  cudaEventRecord(e0, ctx->stream);
+  for (int i = 0; i < n; ++i) k_intr_sweep<<<p->n_items, kWarps * 32, 0, ctx->stream>>>(p->dev, nullptr);
+  cudaEventRecord(e1, ctx->stream);
+  ctx->launches += n + 1;
+  CCG_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / (float)n;
+  CCG_CUDA(ctx, cudaGetLastError());
+  return CCG_OK;
+}
+
+int ccg_intrinsics_download(ccg_intr_problem* p, double* intr, double* q, double* t,
+                            ccg_report* reports) {
+  if (!p) return CCG_ERR_BAD_ARG;
+  return download_problem(p, intr, q, t, reports);
+}
+
+int ccg_intrinsics_history(ccg_intr_problem* p, int64_t b, double* rows, int cap, int* n_rows) {
+  if (!p || b < 0 || b >= p->n_problems || !rows || !n_rows) return CCG_ERR_BAD_ARG;
+  ccg_ctx* ctx = p->ctx;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  IntrState st;
+  CCG_CUDA(ctx, cudaMemcpy(&st, p->dev.ps + b, sizeof(IntrState), cudaMemcpyDeviceToHost));
+  const int total = st.lm.n_hist, n = std::min(std::min(total, kHist), cap);
+  for (int i = 0; i < n; ++i) {
+    const int src = (total - n + i) % kHist;
+    for (int k = 0; k < 6; ++k) rows[i * 6 + k] = st.lm.hist[src][k];
+  }
+  *n_rows = n;
+  return CCG_OK;
+}
+
+int64_t ccg_intrinsics_device_bytes(const ccg_intr_problem* p) { return p ? p->bytes : 0; }
+
+void ccg_intrinsics_destroy(ccg_intr_problem* p) { free_problem(p); }
+
+int ccg_intrinsics_solve_batch(ccg_ctx* ctx, const float* u, const float* v, const float* X,
+                               const float* Y, const float* Z, const int64_t* view_offsets,
+                               int64_t n_views, const int64_t* problem_offsets,
+                               int64_t n_problems, double* intr, double* q, double* t,
+                               uint32_t const_intr_mask, const ccg_opts* opts,
+                               ccg_report* reports) {
+  ccg_intr_problem* p = nullptr;
+  int rc = ccg_intrinsics_create(ctx, u, v, X, Y, Z, view_offsets, n_views, problem_offsets, n_problems,
+                                 intr, q, t, const_intr_mask, 0, &p);
+  if (rc != CCG_OK) return rc;
+  rc = ccg_intrinsics_run(p, opts, nullptr);
+  if (rc == CCG_OK) rc = download_problem(p, intr, q, t, reports);
+  free_problem(p);
+  return rc;
+}
+
+int ccg_intrinsics_solve(ccg_ctx* ctx, const float* u, const float* v, const float* X,
+                         const float* Y, const float* Z, const int64_t* view_offsets,
+                         int64_t n_views, double* intr, double* q, double* t,
+                         uint32_t const_intr_mask, const ccg_opts* opts, ccg_report* report) {
+  const int64_t poff[2] = {0, n_views};
+  return ccg_intrinsics_solve_batch(ctx, u, v, X, Y, Z, view_offsets, n_views, poff, 1, intr, q, t,
+                                    const_intr_mask, opts, report);
+}
+
+int ccg_intrinsics_eval(ccg_ctx* ctx, const float* u, const float* v, const float* X,
+                        const float* Y, const float* Z, const int64_t* view_offsets,
+                        int64_t n_views, const double* intr, const double* q, const double* t,
+                        double* res, double* Vb, double* Wb, double* gvb, double* U, double* gu,
+                        double* cost) {
+  ccg_intr_problem* p = nullptr;
+  const int64_t poff[2] = {0, n_views};
+  int rc = ccg_intrinsics_create(ctx, u, v, X, Y, Z, view_offsets, n_views, poff, 1, intr, q, t, 0, 0, &p);
+  if (rc != CCG_OK) return rc;
+  auto body = [&]() -> int {
+    ccg_opts o;
+    ccg_default_opts(&o);
+    const LmParams P = to_params(o);
+    CCG_TRY(reset_problem(p, P));
+    double* d_res = nullptr;
+    if (res) CCG_TRY(dev_alloc(p, &d_res, (size_t)p->n_obs * 2));
+    Profiler prof;
+    prof.ctx = ctx;
+    int nar = 0;
+    CCG_TRY(launch_sweep_decide(p, P, prof, d_res, &nar));
+    CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CCG_CUDA(ctx, cudaGetLastError());
+    // the first sweep wrote the blocks of the (accepted) initial point into buffer 1
+    std::vector<double> blk((size_t)n_views * kBlk);
+    CCG_CUDA(ctx, cudaMemcpy(blk.data(), p->dev.blk[1], sizeof(double) * blk.size(), cudaMemcpyDeviceToHost));
+    IntrState st;
+    CCG_CUDA(ctx, cudaMemcpy(&st, p->dev.ps, sizeof(IntrState), cudaMemcpyDeviceToHost));
+    if (res) CCG_CUDA(ctx, cudaMemcpy(res, d_res, sizeof(double) * 2 * p->n_obs, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n_views; ++i) {
+      const double* b = &blk[(size_t)i * kBlk];
+      if (Vb) {
+        int idx = 0;
+        for (int a = 0; a < 6; ++a)
+          for (int c = a; c < 6; ++c) {
+            Vb[i * 36 + a * 6 + c] = b[idx];
+            Vb[i * 36 + c * 6 + a] = b[idx];
+            ++idx;
+          }
+      }
+      if (gvb) for (int a = 0; a < 6; ++a) gvb[i * 6 + a] = b[21 + a];
+      if (Wb)
+        for (int a = 0; a < 6; ++a) {
+          for (int c = 0; c < 4; ++c) Wb[i * 54 + a * 9 + c] = b[27 + a * 4 + c];
+          for (int c = 0; c < 5; ++c) Wb[i * 54 + a * 9 + 4 + c] = b[51 + a * 5 + c];
+        }
+    }
+    if (U) std::memcpy(U, st.U, sizeof(double) * 81);
+    if (gu) std::memcpy(gu, st.gu, sizeof(double) * 9);
+    if (cost) *cost = st.lm.cost;
+    return CCG_OK;
+  };
+  rc = body();
+  free_problem(p);
+  return rc;
+}
+
+}  // extern "C"

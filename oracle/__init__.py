@@ -44,6 +44,7 @@ class Opts(C.Structure):
         ("gradient_tolerance", C.c_double),
         ("parameter_tolerance", C.c_double),
         ("huber_a", C.c_double),
+        ("noise_factor", C.c_double),
     ]
 
 

@@ -68,6 +68,21 @@ static inline double clampd(double x, double lo, double hi) { return std::min(st
 
 // relative cost noise allowed when taking a final sub-resolution step
 static const double kNoise = 1e-12;
+static const double kHalfEps = 1.1102230246251565e-16;
+static const int kBlindSteps = 2;
+
+// Rounding noise of the FP64 cost: every residual is a difference of numbers of
+// size `meas_scale` (pixels ~1e3), so it carries ~eps*meas_scale absolute error
+// and the cost ~eps*meas_scale*||r||.  A step whose PREDICTED decrease is below
+// `noise_factor` times that cannot be validated by the gain ratio.
+static inline double cost_noise(const oracle_opts& O, double meas_scale, double rnorm) {
+  return O.noise_factor * kHalfEps * meas_scale * rnorm;
+}
+static double max_abs(const float* a, int64_t n) {
+  float m = 0.0f;
+  for (int64_t i = 0; i < n; ++i) m = std::max(m, std::fabs(a[i]));
+  return (double)m;
+}
 
 // =========================================================================
 //                       single-camera problem
@@ -190,6 +205,7 @@ static int solve_single(const SingleData& D, double* intr, double* q, double* t,
                         const oracle_opts& O, oracle_report* R) {
   const int64_t nv = D.nv;
   const int64_t nobs = D.nobs();
+  const double meas_scale = std::max(max_abs(D.u + D.voff[0], nobs), max_abs(D.v + D.voff[0], nobs));
   SingleEval E;
   eval_single(D, intr, q, t, &E, nullptr);
   oracle_report rep;
@@ -197,6 +213,7 @@ static int solve_single(const SingleData& D, double* intr, double* q, double* t,
   rep.sweeps = 1;
   rep.initial_cost = E.cost;
   double radius = O.initial_radius, nu = 2.0;
+  int blind = 0;  // sub-resolution steps taken so far
   std::vector<double> Y((size_t)nv * 54), z((size_t)nv * 6), dv((size_t)nv * 6), Dv((size_t)nv * 6);
   std::vector<double> qc((size_t)nv * 4), tc((size_t)nv * 3);
   rep.termination = 4;
@@ -297,7 +314,8 @@ static int solve_single(const SingleData& D, double* intr, double* q, double* t,
     // A step this small changes the cost by less than FP64 can resolve, so the
     // gain ratio cannot validate it: take it if the cost does not rise above
     // rounding noise, then stop.
-    const bool tiny = std::sqrt(dDd) <= O.parameter_tolerance * rnorm;
+    const bool tiny = model <= cost_noise(O, meas_scale, rnorm) ||
+                      std::sqrt(dDd) <= O.parameter_tolerance * rnorm;
     double ic[9];
     for (int k = 0; k < 9; ++k) ic[k] = intr[k] + du[k];
     for (int64_t iv = 0; iv < nv; ++iv) {
@@ -309,19 +327,26 @@ static int solve_single(const SingleData& D, double* intr, double* q, double* t,
     if (O.verbose)
       std::printf("[oracle] it %3d cost %.17g cand %.17g rho %.3e radius %.3e |g| %.3e |d| %.3e\n", it,
                   E.cost, cc, rho, radius, gn / rnorm, std::sqrt(dDd) / rnorm);
-    if (tiny) {
-      if (std::isfinite(cc) && cc <= E.cost * (1.0 + kNoise)) {
+    if (tiny || blind > 0) {
+      // sub-resolution step: taken unless the cost rises; one more polishing step follows
+      bool took = false;
+      if (std::isfinite(cc) && cc <= E.cost * (1.0 + kNoise) + 4.0 * cost_noise(O, meas_scale, rnorm)) {
         std::memcpy(intr, ic, sizeof(ic));
         std::memcpy(q, qc.data(), sizeof(double) * (size_t)nv * 4);
         std::memcpy(t, tc.data(), sizeof(double) * (size_t)nv * 3);
         rep.accepted++;
         eval_single(D, intr, q, t, &E, nullptr);
         rep.sweeps++;
+        took = true;
       } else {
         rep.rejected++;
       }
-      rep.termination = 3;
-      break;
+      ++blind;
+      if (!took || blind >= kBlindSteps) {
+        rep.termination = 3;
+        break;
+      }
+      continue;
     }
     if (std::isfinite(cc) && model > 0.0 && rho > O.min_relative_decrease) {
       const double old = E.cost;
@@ -514,6 +539,7 @@ static int solve_rig(const RigData& D, double* qc, double* tc, const uint8_t* fr
                      double* tf, double* obs_cost, const oracle_opts& O, oracle_report* R) {
   const int nc = D.nc, n6 = 6 * nc;
   const int64_t nf = D.nf, nobs = D.nobs();
+  const double meas_scale = std::max(max_abs(D.u + D.foff[0], nobs), max_abs(D.v + D.foff[0], nobs));
   RigEval E;
   eval_rig(D, qc, tc, qf, tf, &E, nullptr);
   oracle_report rep;
@@ -522,6 +548,7 @@ static int solve_rig(const RigData& D, double* qc, double* tc, const uint8_t* fr
   rep.initial_cost = E.cost;
   rep.termination = 4;
   double radius = O.initial_radius, nu = 2.0;
+  int blind = 0;  // sub-resolution steps taken so far
   std::vector<double> Y((size_t)nf * 6 * n6), z((size_t)nf * 6), dv((size_t)nf * 6), Dv((size_t)nf * 6);
   std::vector<double> S((size_t)n6 * n6), rhs(n6), Du(n6), du(n6);
   std::vector<double> qcc((size_t)nc * 4), tcc((size_t)nc * 3), qfc((size_t)nf * 4), tfc((size_t)nf * 3);
@@ -615,7 +642,8 @@ static int solve_rig(const RigData& D, double* qc, double* tc, const uint8_t* fr
         dDd += s * s * Dv[(size_t)f * 6 + a];
       }
     const double model = 0.5 * (lambda * dDd - gTd);
-    const bool tiny = std::sqrt(dDd) <= O.parameter_tolerance * rnorm;  // see solve_single
+    const bool tiny = model <= cost_noise(O, meas_scale, rnorm) ||
+                      std::sqrt(dDd) <= O.parameter_tolerance * rnorm;  // see solve_single
     for (int c = 0; c < nc; ++c) {
       quaternion_plus(qc + c * 4, &du[6 * c], &qcc[(size_t)c * 4]);
       for (int k = 0; k < 3; ++k) tcc[(size_t)c * 3 + k] = tc[c * 3 + k] + du[6 * c + 3 + k];
@@ -629,8 +657,9 @@ static int solve_rig(const RigData& D, double* qc, double* tc, const uint8_t* fr
     if (O.verbose)
       std::printf("[oracle-rig] it %3d cost %.17g cand %.17g rho %.3e radius %.3e |g| %.3e |d| %.3e\n",
                   it, E.cost, cc, rho, radius, gn / rnorm, std::sqrt(dDd) / rnorm);
-    if (tiny) {
-      if (std::isfinite(cc) && cc <= E.cost * (1.0 + kNoise)) {
+    if (tiny || blind > 0) {
+      bool took = false;
+      if (std::isfinite(cc) && cc <= E.cost * (1.0 + kNoise) + 4.0 * cost_noise(O, meas_scale, rnorm)) {
         std::memcpy(qc, qcc.data(), sizeof(double) * (size_t)nc * 4);
         std::memcpy(tc, tcc.data(), sizeof(double) * (size_t)nc * 3);
         std::memcpy(qf, qfc.data(), sizeof(double) * (size_t)nf * 4);
@@ -638,11 +667,16 @@ static int solve_rig(const RigData& D, double* qc, double* tc, const uint8_t* fr
         rep.accepted++;
         eval_rig(D, qc, tc, qf, tf, &E, nullptr);
         rep.sweeps++;
+        took = true;
       } else {
         rep.rejected++;
       }
-      rep.termination = 3;
-      break;
+      ++blind;
+      if (!took || blind >= kBlindSteps) {
+        rep.termination = 3;
+        break;
+      }
+      continue;
     }
     if (std::isfinite(cc) && model > 0.0 && rho > O.min_relative_decrease) {
       const double old = E.cost;
@@ -697,9 +731,10 @@ void oracle_default_opts(oracle_opts* o) {
   o->min_relative_decrease = 1e-3;
   o->min_diagonal = 1e-6;
   o->max_diagonal = 1e32;
-  o->function_tolerance = 1e-14;
+  o->function_tolerance = 1e-16;
   o->gradient_tolerance = 1e-12;
-  o->parameter_tolerance = 1e-7;
+  o->parameter_tolerance = 1e-9;
+  o->noise_factor = 4.0;
   o->huber_a = (double)(3.0f / 500.0f);  // extrinsics_calibrator.cpp:176 (float literal)
 }
 

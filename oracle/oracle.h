@@ -41,6 +41,7 @@ typedef struct {
   double gradient_tolerance;    /* sqrt(g' D^-1 g) <= tol * sqrt(2 cost), D = diag(J'J) */
   double parameter_tolerance;   /* sqrt(d' D d) <= tol * sqrt(2 cost): take the step if the cost does not rise, then stop */
   double huber_a;               /* rig only; <= 0 disables the loss */
+  double noise_factor;          /* predicted decrease <= noise_factor*eps/2*max|meas|*sqrt(2 cost): below cost resolution, take the step and stop */
 } oracle_opts;
 
 typedef struct {

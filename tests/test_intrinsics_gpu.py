@@ -1,0 +1,146 @@
+"""GPU parity tests of the single-camera path: libccg.so (through the C-ABI) vs the
+CPU oracle on identical inputs.  Tolerances are BASELINE.json's: relative 1e-6 on
+recovered parameters, 1e-9 on the final RMS reprojection error."""
+import numpy as np
+import pytest
+
+import oracle
+from camera_calibrator_b200 import synth
+from helpers import TOL_PARAM, TOL_RMS, block_err, quat_to_rot, rel_err, start_from_estimate
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_solution(got, ref, poses=True):
+    gi, gq, gt, grep = got
+    ri, rq, rt, rrep = ref
+    assert rel_err(gi, ri, floor=1e-300) <= TOL_PARAM, (gi, ri)
+    assert abs(grep["rms"] - rrep["rms"]) <= TOL_RMS
+    if poses:
+        # rotations compared as matrices (q and -q are the same pose), entries are O(1)
+        assert np.max(np.abs(quat_to_rot(gq) - quat_to_rot(rq))) <= TOL_PARAM
+        assert rel_err(gt, rt, floor=1e-3) <= TOL_PARAM
+
+
+def test_eval_blocks_match_oracle(ctx):
+    """r, V, W, g_v, U, g_u, cost of one sweep at the Estimate() starting point (C1 shape)."""
+    d = oracle.datagen_planar(20, 54)
+    intr, q, t = start_from_estimate(oracle, d)
+    intr[4:] = [-0.03, 0.002, 0.001, -0.0005, 0.0007]  # exercise every Jacobian column
+    g = ctx.intrinsics_eval(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    r = oracle.intrinsics_eval(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    assert np.max(np.abs(g["res"] - r["res"])) <= 1e-9 * max(1.0, np.max(np.abs(r["res"])))
+    assert abs(g["cost"] - r["cost"]) <= 1e-12 * r["cost"]
+    for key in ("U", "gu"):
+        assert block_err(g[key], r[key]) <= 1e-11, key
+    for i in range(d.view_offsets.size - 1):
+        for key in ("V", "W", "gv"):
+            assert block_err(g[key][i], r[key][i]) <= 1e-11, (key, i)
+
+
+def test_solve_c1_from_estimate(ctx):
+    """Config C1: 20 views x 54 points, Estimate() initialisation, all nine intrinsics free."""
+    d = oracle.datagen_planar(20, 54)
+    intr, q, t = start_from_estimate(oracle, d)
+    got = ctx.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    ref = oracle.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    assert got[3]["termination"] in (1, 2, 3)
+    _check_solution(got, ref)
+    # inputs untouched, counts preserved
+    assert got[1].shape == (20, 4) and got[2].shape == (20, 3)
+
+
+def test_solve_reference_test_scenario(ctx):
+    """The reference's own test (test_calibrator.cpp:45-75): 5 views x 100 points, K within 1 %."""
+    d = oracle.datagen_planar(5, 100)
+    intr, q, t = start_from_estimate(oracle, d)
+    gi, _, _, rep = ctx.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    K = oracle.FIXTURE_K
+    for got, want in ((gi[0], K[0, 0]), (gi[1], K[1, 1]), (gi[2], K[0, 2]), (gi[3], K[1, 2])):
+        assert (got - want) / want < 0.01
+    ref = oracle.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    _check_solution((gi, _, _, rep), ref, poses=False)
+
+
+def test_solve_frozen_k3(ctx):
+    """Python caller's variant: ForceDistortionToConstant(4) freezes k3 (cam_calibration.py:308)."""
+    d = oracle.datagen_planar(12, 54, seed=5)
+    intr, q, t = start_from_estimate(oracle, d)
+    mask = 1 << 8
+    got = ctx.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t, const_mask=mask)
+    ref = oracle.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t, const_mask=mask)
+    assert got[0][8] == 0.0  # frozen coordinate untouched, bit-exact
+    _check_solution(got, ref)
+
+
+def test_solve_ragged_and_empty_views(ctx):
+    """Views of different sizes, including an empty one and one smaller than a warp."""
+    d = oracle.datagen_planar(10, 64, seed=2)
+    intr, q, t = start_from_estimate(oracle, d)
+    keep = [64, 33, 7, 64, 0, 50, 64, 1, 40, 64]
+    idx = np.concatenate([np.arange(i * 64, i * 64 + k) for i, k in enumerate(keep)])
+    off = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
+    u, v, X, Y, Z = (a[idx] for a in (d.u, d.v, d.X, d.Y, d.Z))
+    g = ctx.intrinsics_eval(u, v, X, Y, Z, off, intr, q, t)
+    r = oracle.intrinsics_eval(u, v, X, Y, Z, off, intr, q, t)
+    assert g["res"].shape == r["res"].shape == (int(off[-1]), 2)
+    assert abs(g["cost"] - r["cost"]) <= 1e-12 * r["cost"]
+    assert block_err(g["U"], r["U"]) <= 1e-11
+    assert np.all(g["V"][4] == 0.0) and np.all(g["W"][4] == 0.0)  # empty view contributes nothing
+    got = ctx.intrinsics_solve(u, v, X, Y, Z, off, intr, q, t)
+    ref = oracle.intrinsics_solve(u, v, X, Y, Z, off, intr, q, t)
+    # the empty / 1-point views have free gauge directions: compare intrinsics and RMS only
+    _check_solution(got, ref, poses=False)
+
+
+def test_solve_c2_perturbed_start(ctx):
+    """Config C2 shape (2000 views x 187 points) from the perturbed ground-truth start."""
+    d = synth.planar_views(2000, 187, seed=0)
+    intr, q, t = synth.perturbed_start(d)
+    got = ctx.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    ref = oracle.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    _check_solution(got, ref)
+
+
+def test_solve_batch_matches_individual(ctx):
+    """Config C4 shape, reduced: 24 independent problems (50 views x 54 points, seed = index)."""
+    nb = 24
+    ds = [oracle.datagen_planar(50, 54, seed=b) for b in range(nb)]
+    starts = [start_from_estimate(oracle, d) for d in ds]
+    u, v, X, Y, Z = (np.concatenate([getattr(d, k) for d in ds]) for k in "uvXYZ")
+    off = np.arange(nb * 50 + 1, dtype=np.int64) * 54
+    poff = np.arange(nb + 1, dtype=np.int64) * 50
+    intr = np.stack([s[0] for s in starts])
+    q = np.concatenate([s[1] for s in starts])
+    t = np.concatenate([s[2] for s in starts])
+    gi, gq, gt, greps = ctx.intrinsics_solve(u, v, X, Y, Z, off, intr, q, t, problem_offsets=poff)
+    ri, rq, rt, rreps = oracle.intrinsics_solve_batch(u, v, X, Y, Z, off, poff, intr, q, t)
+    for b in range(nb):
+        sl = slice(b * 50, (b + 1) * 50)
+        _check_solution((gi[b], gq[sl], gt[sl], greps[b]), (ri[b], rq[sl], rt[sl], rreps[b]))
+
+
+def test_device_resident_run_is_repeatable(ctx):
+    """Upload once, run twice: bit-identical results (fixed-order reductions)."""
+    d = synth.planar_views(300, 100, seed=7)
+    intr, q, t = synth.perturbed_start(d)
+    p = ctx.intrinsics_problem(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+    p.run()
+    a = p.download()
+    p.run()
+    b = p.download()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3][0]["final_cost"] == b[3][0]["final_cost"]
+    p.close()
+
+
+def test_bad_arguments_are_rejected(ctx):
+    import camera_calibrator_b200 as cc
+
+    d = oracle.datagen_planar(3, 10)
+    intr, q, t = start_from_estimate(oracle, d)
+    off = d.view_offsets.copy()
+    off[1] = off[2] + 1  # not monotone
+    with pytest.raises(cc.CcgError) as e:
+        ctx.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, off, intr, q, t)
+    assert e.value.status == -1
