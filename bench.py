@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the LM reprojection-error hot path (BASELINE.json metric:
+residual+Jacobian observations/s; LM iterations/s; full calibration wall time).
+
+  python bench.py --gpus N --steps K --warmup W [--workload c5|c2|c4|c1] [--impl reference]
+
+One STEP = one full device-resident Levenberg-Marquardt solve (reset to the
+initial parameters, then residual+Jacobian+normal-equation sweeps, pose
+elimination, reduced solves and accept/reject until convergence) of the
+workload.  `value` = observations x sweeps / device time, inputs resident in
+HBM; `e2e` = the same through the C-ABI call with host buffers (H2D + solve +
+D2H inside the timed region).  Default workload: BASELINE.json configs[4]
+geometry on ONE GPU — a single calibration of 100,000 views x 400 points
+(4e7 observations, 800 MB of observations: larger than the 126 MB L2, so every
+sweep streams from HBM; configs[1] is 7.5 MB and L2-resident).
+With --gpus N > 1 the same 100,000 views are partitioned by view over the N
+GPUs of the box (strong scaling) and every LM iteration all-reduces the packed
+reduced system over NCCL inside libccg.so.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (views, points per view, problems)
+    "c1": (20, 54, 1),
+    "c2": (2000, 187, 1),
+    "c4": (50, 54, 4096),
+    "c5": (100000, 400, 1),
+}
+FLOP_PER_OBS = 716.0  # FP64 flops per observation per sweep of the current kernel pair
+
+
+def algorithmic_bytes(n_obs, n_views):
+    """20 B/observation (u,v,X,Y,Z float32) + per view 56 B pose read and
+    648 B of pose blocks (V 21, W 54, g 6 doubles) written."""
+    return 20.0 * n_obs + 704.0 * n_views
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned(a):
+    """Copy a numpy array into page-locked host memory (torch is plumbing only)."""
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    try:
+        return t.pin_memory().numpy()
+    except RuntimeError:
+        return t.numpy()
+
+
+def make_workload(name, rank, world, scaling):
+    from camera_calibrator_b200 import synth
+
+    V, P, B = WORKLOADS[name]
+    if B == 1:
+        if scaling == "weak":
+            total = V * world
+        else:
+            total = V
+        a, b = total * rank // world, total * (rank + 1) // world
+        d = synth.planar_views(total, P, seed=0, view_range=(a, b))
+        intr, q, t = synth.perturbed_start(d, n_views_total=total, view_start=a)
+        return dict(d=d, intr=intr, q=q, t=t, poff=None, shared=world > 1, total_views=total,
+                    total_obs=total * P, n_problems=1)
+    # batch of independent problems: shard the problems over the ranks, no communication
+    b0, b1 = B * rank // world, B * (rank + 1) // world
+    ds, intrs, qs, ts = [], [], [], []
+    for b in range(b0, b1):
+        d = synth.planar_views(V, P, seed=b)
+        i0, q0, t0 = synth.perturbed_start(d, seed=1000 + b)
+        ds.append(d), intrs.append(i0), qs.append(q0), ts.append(t0)
+    cat = lambda k: np.concatenate([getattr(x, k) for x in ds])
+    nb = b1 - b0
+    d = synth.PlanarViews(cat("u"), cat("v"), cat("X"), cat("Y"), cat("Z"),
+                          np.arange(nb * V + 1, dtype=np.int64) * P, cat("q_true"), cat("t_true"))
+    return dict(d=d, intr=np.stack(intrs), q=np.concatenate(qs), t=np.concatenate(ts),
+                poff=np.arange(nb + 1, dtype=np.int64) * V, shared=False, total_views=B * V,
+                total_obs=B * V * P, n_problems=nb)
+
+
+# ------------------------------------------------------------------ CPU arms
+def cpu_sample(name):
+    """Bounded sample of the workload for the CPU legs (about 10-30 s of host work)."""
+    from camera_calibrator_b200 import synth
+
+    V, P, B = WORKLOADS[name]
+    if B == 1:
+        nv = min(V, 6000)
+        d = synth.planar_views(V, P, seed=0, view_range=(0, nv))
+        intr, q, t = synth.perturbed_start(d, n_views_total=V, view_start=0)
+        return d, intr, q, t, None, f"first {nv} of {V} views x {P} points of the same data set ({nv * P} observations), full LM solve"
+    nb = 24
+    ds = [synth.planar_views(V, P, seed=b) for b in range(nb)]
+    st = [synth.perturbed_start(x, seed=1000 + b) for b, x in enumerate(ds)]
+    cat = lambda k: np.concatenate([getattr(x, k) for x in ds])
+    d = synth.PlanarViews(cat("u"), cat("v"), cat("X"), cat("Y"), cat("Z"),
+                          np.arange(nb * V + 1, dtype=np.int64) * P, cat("q_true"), cat("t_true"))
+    return (d, np.stack([s[0] for s in st]), np.concatenate([s[1] for s in st]),
+            np.concatenate([s[2] for s in st]), np.arange(nb + 1, dtype=np.int64) * V,
+            f"first {nb} of {B} problems ({nb * V * P} observations), full LM solves")
+
+
+def cpu_solve_once(sample):
+    import oracle
+
+    d, intr, q, t, poff, _ = sample
+    t0 = time.perf_counter()
+    if poff is None:
+        _, _, _, rep = oracle.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
+        sweeps_obs = d.n_obs * rep["sweeps"]
+        iters = rep["iterations"]
+    else:
+        _, _, _, reps = oracle.intrinsics_solve_batch(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, poff, intr, q, t)
+        per = d.n_obs // len(reps)
+        sweeps_obs = sum(per * r["sweeps"] for r in reps)
+        iters = sum(r["iterations"] for r in reps)
+    dt = time.perf_counter() - t0
+    return sweeps_obs / dt, dt, iters
+
+
+def run_reference(args):
+    """--impl reference: the restated reference algorithm (oracle port; the reference itself
+    cannot be compiled here — Ceres/Eigen/OpenCV absent) on the host cores, all threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    oracle.build()
+    sample = cpu_sample(args.workload)
+    cores = oracle.num_threads()
+    for _ in range(min(args.warmup, 1)):
+        cpu_solve_once(sample)
+    vals, times = [], []
+    for _ in range(args.steps):
+        v, dt, _ = cpu_solve_once(sample)
+        vals.append(v), times.append(dt)
+    V, P, B = WORKLOADS[args.workload]
+    value = float(np.sum([v * t for v, t in zip(vals, times)]) / np.sum(times))
+    line = {
+        "impl": "reference", "metric": "residual+Jacobian observations/s (full LM solve)", "value": value,
+        "unit": "obs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, args.gpus, args.scaling),
+        "cpu_baseline": {"value": value, "unit": "obs/s", "cores": cores, "kind": "port", "sample": sample[5]},
+        "e2e": {"value": value, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, gpus, scaling):
+    V, P, B = WORKLOADS[name]
+    desc = {
+        "c1": "BASELINE configs[0]: single-camera calibration, 20 views x 54 points",
+        "c2": "BASELINE configs[1]: single-camera intrinsics+distortion, 2000 views x 187 points (L2-resident)",
+        "c4": "BASELINE configs[3]: 4096 independent calibrations (50 views x 54 points), sharded by problem",
+        "c5": "BASELINE configs[4] geometry: single calibration, 100000 views x 400 points (4e7 observations), "
+              "view-partitioned over the GPUs with an NCCL allreduce of the reduced system per LM iteration",
+    }[name]
+    return {"workload": desc, "views": V, "points_per_view": P, "problems": B,
+            "parallelism": f"view-partition x{gpus}" if B == 1 else f"problem-shard x{gpus}",
+            "start": "ground-truth poses perturbed +-0.02 / +-1 deg, K off by +-2 % / +-10 px, zero distortion",
+            "cache": "inputs larger than L2 (no flush needed)" if name in ("c5", "c4") else
+                     "inputs smaller than L2: L2-resident after the first sweep (roofline not meaningful)"}
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import camera_calibrator_b200 as cc
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    ctx = cc.Context(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.tensor(list(cc.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(rank, world, bytes(uid.cpu().tolist()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+            ctx.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tns, op=dist.ReduceOp.SUM)
+        return float(tns.item())
+
+    wl = make_workload(args.workload, rank, world, args.scaling)
+    d = wl["d"]
+    opts = cc.default_opts(profile=1)
+    prob = ctx.intrinsics_problem(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, wl["intr"], wl["q"], wl["t"],
+                                  problem_offsets=wl["poff"], shared=wl["shared"])
+    fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0
+
+    # ---- device-resident solves: W warm-up, K timed
+    for _ in range(args.warmup):
+        prob.run(opts)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches()
+    tot_ms = sweep_ms = schur_ms = small_ms = 0.0
+    n_sweeps = n_allreduce = 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        tm = prob.run(opts)
+        tot_ms += tm["total_ms"]
+        sweep_ms += tm["sweep_ms"]
+        schur_ms += tm["schur_ms"]
+        small_ms += tm["small_ms"]
+        n_sweeps += tm["sweep_launches"]
+        n_allreduce += tm["allreduces"]
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    intr, q, t, reps = prob.download()
+    # observations swept per step over the whole job (every problem: its obs x its sweeps)
+    if wl["poff"] is None:
+        obs_sweeps_local = d.n_obs * reps[0]["sweeps"]
+    else:
+        per = d.n_obs // max(len(reps), 1)
+        obs_sweeps_local = sum(per * r["sweeps"] for r in reps)
+    obs_sweeps = allsum(float(obs_sweeps_local))
+    tot_ms = allmax(tot_ms)
+    ms_per_step = tot_ms / args.steps
+    value = obs_sweeps / (ms_per_step * 1e-3)
+    iters = reps[0]["iterations"] if wl["poff"] is None else allsum(float(sum(r["iterations"] for r in reps)))
+
+    # ---- dominant kernel against the roofline (this rank's share, rank 0 reports)
+    sweep_ms_avg = sweep_ms / max(n_sweeps, 1)
+    alg_bytes = algorithmic_bytes(d.n_obs, d.n_views)
+    hbm_peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (sweep_ms_avg * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = tj.get(args.workload, {}).get("k_intr_sweep_dram_bytes_per_launch")
+
+    # ---- end to end through the C-ABI with host buffers (H2D + solve + D2H timed)
+    hu, hv, hX, hY, hZ = (pinned(a) for a in (d.u, d.v, d.X, d.Y, d.Z))
+    e2e_opts = cc.default_opts()
+    h2d = 20 * d.n_obs + 8 * (d.n_views + 1) + 8 * 7 * d.n_views + 8 * 9 * wl["n_problems"]
+    d2h = 8 * 7 * d.n_views + (8 * 9 + 56) * wl["n_problems"]
+    e2e_times = []
+    n_e2e = max(1, min(args.steps, 3))
+    for i in range(1 + n_e2e):
+        barrier()
+        t0 = time.perf_counter()
+        r = ctx.intrinsics_solve(hu, hv, hX, hY, hZ, d.view_offsets, wl["intr"], wl["q"], wl["t"],
+                                 opts=e2e_opts, problem_offsets=wl["poff"]) if not wl["shared"] else None
+        if wl["shared"]:
+            p2 = ctx.intrinsics_problem(hu, hv, hX, hY, hZ, d.view_offsets, wl["intr"], wl["q"], wl["t"], shared=True)
+            p2.run(e2e_opts)
+            r = p2.download()
+            p2.close()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_times.append(dt)
+    e2e_t = allmax(float(np.mean(e2e_times)))
+    e2e_value = obs_sweeps / e2e_t
+
+    line = None
+    if rank == 0:
+        # CPU baseline: oracle port on a bounded sample of the same workload, all host threads
+        import oracle
+
+        oracle.build()
+        sample = cpu_sample(args.workload)
+        cpu_v, cpu_dt, _ = cpu_solve_once(sample)
+        line = {
+            "metric": "residual+Jacobian observations/s (full LM solve)", "value": value, "unit": "obs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": args.scaling if wl["poff"] is None else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, world, args.scaling),
+            "lm_iterations_per_s": iters / (ms_per_step * 1e-3),
+            "full_solve_wall_ms": wall_ms / args.steps,
+            "solve": {"iterations": reps[0]["iterations"], "sweeps": reps[0]["sweeps"],
+                      "rejected": reps[0]["rejected"], "termination": reps[0]["termination"],
+                      "rms_px": reps[0]["rms"], "gradient_norm": reps[0]["gradient_norm"],
+                      "intrinsics": [float(x) for x in intr[0]]},
+            "breakdown_ms_per_step": {"sweep": sweep_ms / args.steps, "eliminate": schur_ms / args.steps,
+                                      "reduce+decide+solve(+allreduce)": small_ms / args.steps,
+                                      "allreduces_per_step": n_allreduce / args.steps},
+            "roofline": {"kernel": "k_intr_sweep", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                         "peak_source": peak_src, "launch_ms": sweep_ms_avg, "launches": n_sweeps,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "fp64": {"achieved_tflops": FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
+                                  "peak_tflops": fp64_peak, "flop_per_obs": FLOP_PER_OBS,
+                                  "peak_source": "DFMA micro-benchmark run in this process"}},
+            "cpu_baseline": {"value": cpu_v, "unit": "obs/s", "cores": oracle.num_threads(), "kind": "port",
+                             "sample": sample[5], "seconds": cpu_dt},
+            "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": int(allsum(float(h2d))) if world > 1 else int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_t * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+    else:
+        allsum(float(h2d))
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    prob.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,7 +31,7 @@ constexpr int kBlk = 84;        // per-view block stride (doubles): V21 | gv6 | 
 constexpr int kYz = 72;         // per-view elimination record: Y 54 | z 6 | gv 6 | Dv 6
 constexpr int kPose = 8;        // q4 t3 pad
 constexpr int kSweepPart = 64;  // per-item sweep partial (doubles)
-constexpr int kSchurPart = 96;  // per-item elimination partial
+constexpr int kSchurPart = 64;  // per-item elimination partial: S upper 45 | rhs 9 | g'D^-1g | fails
 constexpr int kWarps = 8;       // warps per CTA (4 view pairs in the sweep, 8 views in the elimination)
 
 // sweep partial layout
@@ -116,6 +116,24 @@ __device__ __forceinline__ void obs_geometry(const double (&R)[9], const double 
   g.jv[5] = -(B0 * xn + B1 * yn);
 }
 
+// one observation's five float32 fields, fetched ahead of use
+struct ObsLoad {
+  float mu, mv, X, Y, Z;
+  int64_t o;
+  bool valid;
+  __device__ __forceinline__ void fetch(const IntrDev& d, int64_t idx, int64_t end) {
+    o = idx;
+    valid = idx < end;
+    if (valid) {
+      mu = __ldg(d.u + idx);
+      mv = __ldg(d.v + idx);
+      X = __ldg(d.X + idx);
+      Y = __ldg(d.Y + idx);
+      Z = __ldg(d.Z + idx);
+    }
+  }
+};
+
 // Candidate pose of a view: current pose (+) delta_v, delta_v = -z - Y du.
 // Returns R, t of the candidate; lanes 0..5 of warp A also return their share
 // of g'd and d'Dd; warp A stores the candidate pose.
@@ -192,10 +210,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep(IntrDev d, double
 #pragma unroll
       for (int i = 0; i < 51; ++i) acc[i] = 0.0;
       const int64_t o1 = d.view_off[v + 1];
-      for (int64_t o = d.view_off[v] + lane; o < o1; o += 32) {
-        const float mu = __ldg(d.u + o), mv = __ldg(d.v + o);
+      // software-pipelined: the loads of the next 32 observations are in flight while
+      // this lane works on the current one (8 warps per SM cannot hide HBM latency alone)
+      ObsLoad nx;
+      nx.fetch(d, d.view_off[v] + lane, o1);
+      while (nx.valid) {
+        const ObsLoad cur = nx;
+        const int64_t o = cur.o;
+        nx.fetch(d, o + 32, o1);
+        const float mu = cur.mu, mv = cur.mv;
         ObsGeom g;
-        obs_geometry(R, t, k, __ldg(d.X + o), __ldg(d.Y + o), __ldg(d.Z + o), g);
+        obs_geometry(R, t, k, cur.X, cur.Y, cur.Z, g);
         const double ru = k[0] * g.xd + k[2] - (double)mu;
         const double rv = k[1] * g.yd + k[3] - (double)mv;
         if (res_out) {
@@ -248,10 +273,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep(IntrDev d, double
 #pragma unroll
       for (int i = 0; i < 30; ++i) acc[i] = 0.0;
       const int64_t o1 = d.view_off[v + 1];
-      for (int64_t o = d.view_off[v] + lane; o < o1; o += 32) {
-        const float mu = __ldg(d.u + o), mv = __ldg(d.v + o);
+      // software-pipelined: the loads of the next 32 observations are in flight while
+      // this lane works on the current one (8 warps per SM cannot hide HBM latency alone)
+      ObsLoad nx;
+      nx.fetch(d, d.view_off[v] + lane, o1);
+      while (nx.valid) {
+        const ObsLoad cur = nx;
+        const int64_t o = cur.o;
+        nx.fetch(d, o + 32, o1);
+        const float mu = cur.mu, mv = cur.mv;
         ObsGeom g;
-        obs_geometry(R, t, k, __ldg(d.X + o), __ldg(d.Y + o), __ldg(d.Z + o), g);
+        obs_geometry(R, t, k, cur.X, cur.Y, cur.Z, g);
         const double ru = k[0] * g.xd + k[2] - (double)mu;
         const double rv = k[1] * g.yd + k[3] - (double)mv;
         double au[5], av[5];
@@ -304,11 +336,22 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep(IntrDev d, double
 }
 
 // --------------------------------------------------------------------------
-// pose elimination: per view Cholesky of V + lambda D, Y = V'^-1 W, z = V'^-1 g_v,
-// contributions W'Y and W'z to the reduced system
+// pose elimination, one THREAD per view: Cholesky of V + lambda D, T = L^-1 [W g_v],
+// Y = L^-T T (stored for the back-substitution), contributions T'T and T't_g to the
+// reduced system.  A warp stages 32 consecutive view blocks through shared memory
+// (coalesced global reads/writes, conflict-free odd stride), each lane eliminates
+// one view, and the 56 reduced-system terms are summed across lanes with the
+// transposing shuffle reduction.
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarps * 32) k_intr_schur(IntrDev d, LmParams P) {
-  __shared__ double s_part[kWarps][kSchurPart];
+constexpr int kSchurWarps = 2;
+constexpr int kStage = 85;  // odd stride (doubles) of one staged view block: conflict-free LDS.64
+
+// packed index of (j,k), j <= k, in the 9x9 upper triangle
+__host__ __device__ constexpr int up9(int j, int k) { return j * 9 - j * (j - 1) / 2 + (k - j); }
+
+__global__ void __launch_bounds__(kSchurWarps * 32) k_intr_schur(IntrDev d, LmParams P) {
+  __shared__ double s_stage[kSchurWarps][32 * kStage];
+  __shared__ double s_part[kSchurWarps][kSchurPart];
   __shared__ int s_meta[2];
   __shared__ double s_lambda;
   const WorkItem it = d.items[blockIdx.x];
@@ -323,84 +366,125 @@ __global__ void __launch_bounds__(kWarps * 32) k_intr_schur(IntrDev d, LmParams 
   const int par = s_meta[0];
   const double lambda = s_lambda;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double acc[9];
+  double* stage = s_stage[warp];
+  double racc0 = 0.0, racc1 = 0.0;  // lane L: reduced-system terms L and 32+L
+  for (int64_t base = it.v0 + warp * 32; base < it.v1; base += kSchurWarps * 32) {
+    const int nv = (int)min((int64_t)32, it.v1 - base);
+    const double* blk = d.blk[par] + (size_t)base * kBlk;
+    for (int vi = 0; vi < nv; ++vi)
 #pragma unroll
-  for (int j = 0; j < 9; ++j) acc[j] = 0.0;
-  double gDg = 0.0, fails = 0.0;
-  for (int64_t v = it.v0 + warp; v < it.v1; v += kWarps) {
-    const double* blk = d.blk[par] + (size_t)v * kBlk;
-    double A[6][6], Dv[6], gv[6];
-    {
-      int idx = 0;
+      for (int e = lane; e < 81; e += 32) stage[vi * kStage + e] = blk[vi * kBlk + e];
+    __syncwarp();
+    double vals[64];
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
+    for (int i = 0; i < 64; ++i) vals[i] = 0.0;
+    if (lane < nv) {
+      double* s = stage + lane * kStage;
+      double A[6][6], Dv[6], tg[6];
+      {
+        int idx = 0;
 #pragma unroll
-        for (int b = a; b < 6; ++b) {
-          A[b][a] = blk[idx];
-          ++idx;
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = a; b < 6; ++b) {
+            A[b][a] = s[idx];
+            ++idx;
+          }
+      }
+      double gDg = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        tg[a] = s[21 + a];
+        Dv[a] = clampd(A[a][a], P.min_diagonal, P.max_diagonal);
+        if (A[a][a] > 0.0) gDg += tg[a] * tg[a] / A[a][a];
+        A[a][a] += lambda * Dv[a];
+      }
+      const bool ok = chol6(A);
+      double T[6][9];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) T[a][c] = s[27 + a * 4 + c];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) T[a][4 + c] = s[51 + a * 5 + c];
+      }
+      // record for the sweep prologue: g_v and D_v (the block slots are consumed by now)
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        s[60 + a] = tg[a];
+        s[66 + a] = Dv[a];
+      }
+      // forward substitution: T <- L^-1 W, tg <- L^-1 g_v
+      double inv[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) inv[i] = 1.0 / A[i][i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+#pragma unroll
+          for (int c = 0; c < 9; ++c) T[i][c] -= A[i][k] * T[k][c];
+          tg[i] -= A[i][k] * tg[k];
         }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
+        tg[i] *= inv[i];
+      }
+      // reduced-system terms: (W' V'^-1 W)[j][k] = T[:,j].T[:,k], (W' V'^-1 g)[j] = T[:,j].tg
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+#pragma unroll
+        for (int k = j; k < 9; ++k) {
+          double acc = 0.0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a) acc = fma(T[a][j], T[a][k], acc);
+          vals[up9(j, k)] = acc;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc = fma(T[a][j], tg[a], acc);
+        vals[45 + j] = acc;
+      }
+      vals[54] = gDg;
+      vals[55] = ok ? 0.0 : 1.0;
+      // backward substitution: Y = L^-T T, z = L^-T tg
+#pragma unroll
+      for (int i = 5; i >= 0; --i) {
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) {
+#pragma unroll
+          for (int c = 0; c < 9; ++c) T[i][c] -= A[k][i] * T[k][c];
+          tg[i] -= A[k][i] * tg[k];
+        }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
+        tg[i] *= inv[i];
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) s[a * 9 + c] = T[a][c];
+        s[54 + a] = tg[a];
+      }
     }
+    __syncwarp();
+    double* yz = d.yz + (size_t)base * kYz;
+    for (int vi = 0; vi < nv; ++vi)
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      gv[a] = blk[21 + a];
-      Dv[a] = clampd(A[a][a], P.min_diagonal, P.max_diagonal);
-      if (lane == 0 && A[a][a] > 0.0) gDg += gv[a] * gv[a] / A[a][a];
-      A[a][a] += lambda * Dv[a];
-    }
-    const bool ok = chol6(A);
-    if (!ok && lane == 0) fails += 1.0;
-    // column `lane` of [W | g_v]
-    double col[6];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double w = 0.0;
-      if (lane < 4) w = blk[27 + a * 4 + lane];
-      else if (lane < 9) w = blk[51 + a * 5 + (lane - 4)];
-      else if (lane == 9) w = gv[a];
-      col[a] = w;
-    }
-    double y[6];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) y[a] = col[a];
-    chol6_solve(A, y);
-    double* yz = d.yz + (size_t)v * kYz;
-    if (lane < 9) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a) yz[a * 9 + lane] = y[a];
-    } else if (lane == 9) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a) yz[54 + a] = y[a];
-    } else if (lane == 10) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a) yz[60 + a] = gv[a];
-    } else if (lane == 11) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a) yz[66 + a] = Dv[a];
-    }
-    // acc[j] (lane k) += W[:,j] . y_k   ->  (W'Y)[j][k] for k < 9, (W'z)[j] for k == 9
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s = fma(__shfl_sync(0xffffffffu, col[a], j), y[a], s);
-      acc[j] += s;
-    }
+      for (int e = lane; e < kYz; e += 32) yz[vi * kYz + e] = stage[vi * kStage + e];
+    double out[2];
+    warp_reduce_array<64>(vals, lane, out);
+    racc0 += out[0];
+    racc1 += out[1];
+    __syncwarp();
   }
-  if (lane < 10) {
-#pragma unroll
-    for (int j = 0; j < 9; ++j) s_part[warp][lane * 9 + j] = acc[j];
-  }
-  if (lane == 0) {
-    s_part[warp][90] = gDg;
-    s_part[warp][91] = fails;
-  }
+  s_part[warp][lane] = racc0;
+  s_part[warp][32 + lane] = racc1;
   __syncthreads();
   if (threadIdx.x < kSchurPart) {
     double s = 0.0;
-    if (threadIdx.x < 92) {
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) s += s_part[w][threadIdx.x];
-    }
+    for (int w = 0; w < kSchurWarps; ++w) s += s_part[w][threadIdx.x];
     d.schur_part[(size_t)blockIdx.x * kSchurPart + threadIdx.x] = s;
   }
 }
@@ -511,7 +595,7 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
   const double* r = s_buf;
   const unsigned mask = ps.mask;
   const int par = s.par;
-  double gDg = r[90];
+  double gDg = r[54];
   for (int k = 0; k < 9; ++k)
     if (!((mask >> k) & 1u) && ps.U[k * 9 + k] > 0.0) gDg += ps.gu[k] * ps.gu[k] / ps.U[k * 9 + k];
   const double rnorm = sqrt(2.0 * s.cost);
@@ -525,7 +609,7 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
     return;
   }
   s.iterations++;
-  if (r[91] > 0.0) {
+  if (r[55] > 0.0) {
     s.solve_ok = 0;
     return;
   }
@@ -533,10 +617,9 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
   const double lambda = s.lambda;
   for (int a = 0; a < 9; ++a) {
     Du[a] = clampd(ps.U[a * 9 + a], P.min_diagonal, P.max_diagonal);
-    rhs[a] = -ps.gu[a] + r[81 + a];
+    rhs[a] = -ps.gu[a] + r[45 + a];
     for (int b = 0; b < 9; ++b) {
-      // (W'Y)[a][b] lives at r[b*9 + a]; symmetrise from the upper triangle
-      const double wy = a <= b ? r[b * 9 + a] : r[a * 9 + b];
+      const double wy = a <= b ? r[up9(a, b)] : r[up9(b, a)];  // packed upper triangle of W'V'^-1W
       S[a * 9 + b] = ps.U[a * 9 + b] - wy;
     }
     S[a * 9 + a] += lambda * Du[a];
@@ -786,7 +869,7 @@ int launch_schur_solve(ccg_intr_problem* p, const LmParams& P, Profiler& prof, i
   cudaStream_t st = ctx->stream;
   const int nb = (int)p->n_problems;
   prof.begin(TAG_SCHUR);
-  k_intr_schur<<<p->n_items, kWarps * 32, 0, st>>>(d, P);
+  k_intr_schur<<<p->n_items, kSchurWarps * 32, 0, st>>>(d, P);
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
@@ -816,7 +899,6 @@ int run_problem(ccg_intr_problem* p, const ccg_opts& opts, ccg_timing* timing) {
   ccg_ctx* ctx = p->ctx;
   CCG_CUDA(ctx, cudaSetDevice(ctx->device));
   const LmParams P = to_params(opts);
-  CCG_TRY(reset_problem(p, P));
   Profiler prof;
   prof.ctx = ctx;
   prof.on = opts.profile != 0;
@@ -833,6 +915,7 @@ int run_problem(ccg_intr_problem* p, const ccg_opts& opts, ccg_timing* timing) {
     prof.used = tot.used;
   }
   cudaEventRecord(ctx->events[ev_total0], ctx->stream);
+  CCG_TRY(reset_problem(p, P));  // restoring the initial parameters is part of the timed solve
   CCG_TRY(launch_sweep_decide(p, P, prof, nullptr, &n_allreduce));
   const int poll_every = 4;
   int done = 0;

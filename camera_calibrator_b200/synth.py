@@ -84,9 +84,38 @@ def quat_to_rot(q):
     return R
 
 
+CHUNK_VIEWS = 2048  # views are generated in chunks, chunk c from the stream seeded (seed, c)
+
+
 def planar_views(n_views, n_points, seed=0, K=FIXTURE_K, dist=FIXTURE_DIST, size=FIXTURE_SIZE,
-                 noise_px=0.5, chunk_views=4096) -> PlanarViews:
-    rng = np.random.default_rng(seed)
+                 noise_px=0.5, view_range=None) -> PlanarViews:
+    """Views [view_range[0], view_range[1]) of the `n_views`-view data set `seed` (default: all).
+    Every chunk of CHUNK_VIEWS views has its own random stream, so a rank of a
+    view-partitioned run generates exactly its share and all ranks agree on the whole."""
+    a, b = (0, n_views) if view_range is None else view_range
+    assert 0 <= a <= b <= n_views
+    parts = []
+    for c in range(a // CHUNK_VIEWS, (b - 1) // CHUNK_VIEWS + 1 if b > a else a // CHUNK_VIEWS):
+        c0 = c * CHUNK_VIEWS
+        nvc = min(CHUNK_VIEWS, n_views - c0)
+        part = _planar_chunk(nvc, n_points, np.random.default_rng([seed, c]), K, dist, size, noise_px)
+        lo, hi = max(a, c0) - c0, min(b, c0 + nvc) - c0
+        parts.append(_slice_views(part, lo, hi, n_points))
+    if not parts:
+        z = np.zeros(0, np.float32)
+        return PlanarViews(z, z, z, z, z, np.zeros(1, np.int64), np.zeros((0, 4)), np.zeros((0, 3)))
+    cat = lambda k: np.concatenate([getattr(p, k) for p in parts])
+    off = np.arange(b - a + 1, dtype=np.int64) * n_points
+    return PlanarViews(cat("u"), cat("v"), cat("X"), cat("Y"), cat("Z"), off, cat("q_true"), cat("t_true"))
+
+
+def _slice_views(p, lo, hi, n_points):
+    s = slice(lo * n_points, hi * n_points)
+    off = np.arange(hi - lo + 1, dtype=np.int64) * n_points
+    return PlanarViews(p.u[s], p.v[s], p.X[s], p.Y[s], p.Z[s], off, p.q_true[lo:hi], p.t_true[lo:hi])
+
+
+def _planar_chunk(n_views, n_points, rng, K, dist, size, noise_px, chunk_views=CHUNK_VIEWS) -> PlanarViews:
     w, h = size
     Kinv = np.linalg.inv(K)
     n = n_views * n_points
@@ -146,13 +175,17 @@ def planar_views(n_views, n_points, seed=0, K=FIXTURE_K, dist=FIXTURE_DIST, size
 
 
 def perturbed_start(views: PlanarViews, seed=1, K=FIXTURE_K, trans=0.02, rot_deg=1.0, focal_rel=0.02,
-                    centre_px=10.0):
+                    centre_px=10.0, n_views_total=None, view_start=0):
     """Solver-only starting point: ground-truth poses perturbed by
     U(+-trans) / U(+-rot_deg) per axis, focal lengths off by +-focal_rel, principal
-    point off by +-centre_px, zero distortion (reference default, calibrator.hh:50)."""
+    point off by +-centre_px, zero distortion (reference default, calibrator.hh:50).
+    For a partition, pass the total view count and this partition's first view so
+    that every rank draws the same perturbations for the same views."""
     rng = np.random.default_rng(seed)
     nv = views.n_views
-    ang = np.deg2rad(rng.uniform(-rot_deg, rot_deg, size=(nv, 3))) / 2.0
+    tot = nv if n_views_total is None else n_views_total
+    pert = rng.uniform(-1.0, 1.0, size=(tot, 6))[view_start:view_start + nv]
+    ang = np.deg2rad(rot_deg * pert[:, :3]) / 2.0
     dq = np.concatenate([np.ones((nv, 1)), ang], axis=1)
     dq /= np.linalg.norm(dq, axis=1, keepdims=True)
     q0 = views.q_true
@@ -160,7 +193,7 @@ def perturbed_start(views: PlanarViews, seed=1, K=FIXTURE_K, trans=0.02, rot_deg
     w1, x1, y1, z1 = q0.T
     q = np.stack([w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1, w0 * x1 + x0 * w1 + y0 * z1 - z0 * y1,
                   w0 * y1 - x0 * z1 + y0 * w1 + z0 * x1, w0 * z1 + x0 * y1 - y0 * x1 + z0 * w1], axis=1)
-    t = views.t_true + rng.uniform(-trans, trans, size=(nv, 3))
+    t = views.t_true + trans * pert[:, 3:]
     intr = np.zeros(9)
     intr[0] = K[0, 0] * (1.0 + rng.uniform(-focal_rel, focal_rel))
     intr[1] = K[1, 1] * (1.0 + rng.uniform(-focal_rel, focal_rel))
