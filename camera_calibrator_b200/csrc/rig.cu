@@ -1,0 +1,1063 @@
+// Rig hot path: residual + analytic Jacobian + Huber corrector + normal-equation
+// blocks + Schur elimination of the per-frame rig poses onto the camera
+// extrinsics + device-resident LM loop.
+//
+// Replaces, behind ccg_rig_*:
+//   the per-observation autodiff evaluation of ReprojectionErrorExtrinsics
+//       reference src/extrinsics_calibrator.cpp:51-84
+//   HuberLoss(3.0f/500.0f) per residual block      reference :175-176  [ext Ceres corrector]
+//   the Ceres problem build, ceres::Solve, per-observation final cost
+//       reference src/extrinsics_calibrator.cpp:92-225
+// Layout: the host sorts the observations of every frame by camera (stable) so
+// that a (frame, camera) SEGMENT is contiguous; a warp pair owns a frame and
+// walks its segments: warp A accumulates V_f(21) and U_cc(21), warp B W_fc(36),
+// g_f(6), g_c(6).  Up to kMaxCams cameras (6C+1 columns fit one warp in the
+// elimination kernel).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ccg {
+
+constexpr int kMaxCams = 5;
+constexpr int kMaxN6 = 6 * kMaxCams;          // 30 reduced unknowns at most
+constexpr int kRigWarps = 8;                  // sweep: 4 frame pairs per CTA
+constexpr int kRigPart = 27 * kMaxCams + 9;   // 144: U_cc 21 + g_c 6 per camera | rho sum | sumsq | g'd | d'Dd | n
+constexpr int kRigSchurWarps = 4;
+constexpr int kRigSchurPart = (kMaxN6 + 1) * kMaxN6 + 2;  // 932: (W'Y | W'z) columns x rows | g'D^-1g | fails
+
+struct RigState {
+  LmState lm;
+  double cam[2][kMaxCams][8];  // q4 t3 pad, [par] = current
+  double du[kMaxN6];
+  double Ucc[kMaxCams][21];    // block-diagonal U at the current point (packed upper 6x6)
+  double gc[kMaxCams][6];
+  int frozen[kMaxCams];
+  int n_cams, item0, item1, pad_;
+};
+
+struct RigDev {
+  const float *u, *v;       // sorted by (frame, camera)
+  const int* pt;            // world point id per observation
+  const float* Xw;          // 3 per world point
+  const int64_t* seg_off;   // [F*C + 1]
+  const WorkItem* items;    // frame ranges
+  double* pose[2];          // per frame q4 t3 pad
+  double* blk[2];           // per frame: V21 | g6 | W 6 x 6C
+  double* yz;               // per frame: Y 6 x 6C | z 6 | g 6 | D 6
+  double* sweep_part;
+  double* schur_part;
+  double* red_sweep;
+  double* red_schur;
+  RigState* ps;
+  int* n_done;
+  int n_cams, blk_stride, yz_stride;
+};
+
+// 2 (y x m)
+__device__ __forceinline__ void cross2(const double (&y)[3], const double (&m)[3], double* out) {
+  out[0] = 2.0 * (y[1] * m[2] - y[2] * m[1]);
+  out[1] = 2.0 * (y[2] * m[0] - y[0] * m[2]);
+  out[2] = 2.0 * (y[0] * m[1] - y[1] * m[0]);
+}
+
+struct RigGeom {
+  double ru, rv;        // residual scaled by sqrt(rho')
+  double rho, s;        // robust cost term (rho(s)) and raw squared norm
+  double jfu[6], jfv[6], jcu[6], jcv[6];
+};
+
+__device__ __forceinline__ void rig_geometry(const double (&Rf)[9], const double (&tf)[3],
+                                             const double (&Rc)[9], const double (&tc)[3], double X,
+                                             double Y, double Z, double mu, double mv, double huber_a,
+                                             RigGeom& g) {
+  double yf[3], yc[3];
+  yf[0] = Rf[0] * X + Rf[1] * Y + Rf[2] * Z;
+  yf[1] = Rf[3] * X + Rf[4] * Y + Rf[5] * Z;
+  yf[2] = Rf[6] * X + Rf[7] * Y + Rf[8] * Z;
+  const double p0 = yf[0] + tf[0], p1 = yf[1] + tf[1], p2 = yf[2] + tf[2];
+  yc[0] = Rc[0] * p0 + Rc[1] * p1 + Rc[2] * p2;
+  yc[1] = Rc[3] * p0 + Rc[4] * p1 + Rc[5] * p2;
+  yc[2] = Rc[6] * p0 + Rc[7] * p1 + Rc[8] * p2;
+  const double iz = 1.0 / (yc[2] + tc[2]);
+  const double xn = (yc[0] + tc[0]) * iz, yn = (yc[1] + tc[1]) * iz;
+  double ru = xn - mu, rv = yn - mv;
+  const double s = ru * ru + rv * rv;
+  double rho = s, w = 1.0;
+  if (huber_a > 0.0 && s > huber_a * huber_a) {
+    const double r = sqrt(s);
+    rho = 2.0 * huber_a * r - huber_a * huber_a;
+    w = sqrt(huber_a / r);  // sqrt(rho'): [ext] Ceres corrector for rho'' <= 0
+  }
+  g.s = s;
+  g.rho = rho;
+  g.ru = ru * w;
+  g.rv = rv * w;
+  const double wz = w * iz;
+  // rows of d(xn,yn)/d(camera-frame point), scaled by sqrt(rho')
+  const double m0[3] = {wz, 0.0, -wz * xn};
+  const double m1[3] = {0.0, wz, -wz * yn};
+  cross2(yc, m0, g.jcu);
+  cross2(yc, m1, g.jcv);
+  g.jcu[3] = m0[0]; g.jcu[4] = m0[1]; g.jcu[5] = m0[2];
+  g.jcv[3] = m1[0]; g.jcv[4] = m1[1]; g.jcv[5] = m1[2];
+  // chain through the camera rotation: row * Rc
+  double f0[3], f1[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    f0[j] = m0[0] * Rc[j] + m0[2] * Rc[6 + j];
+    f1[j] = m1[1] * Rc[3 + j] + m1[2] * Rc[6 + j];
+  }
+  cross2(yf, f0, g.jfu);
+  cross2(yf, f1, g.jfv);
+  g.jfu[3] = f0[0]; g.jfu[4] = f0[1]; g.jfu[5] = f0[2];
+  g.jfv[3] = f1[0]; g.jfv[4] = f1[1]; g.jfv[5] = f1[2];
+}
+
+// candidate frame pose = current (+) (-z - Y du)
+__device__ __forceinline__ void frame_prologue(const RigDev& d, int par, int64_t f, int lane, bool is_a,
+                                               const double* s_du, int n6, double (&R)[9],
+                                               double (&t)[3], double& gTd, double& dDd) {
+  const double* yz = d.yz + (size_t)f * d.yz_stride;
+  double dl = 0.0;
+  if (lane < 6) {
+    dl = -yz[6 * n6 + lane];
+    for (int j = 0; j < n6; ++j) dl -= yz[lane * n6 + j] * s_du[j];
+    if (is_a) {
+      gTd += yz[6 * n6 + 6 + lane] * dl;
+      dDd += dl * dl * yz[6 * n6 + 12 + lane];
+    }
+  }
+  const double d0 = __shfl_sync(0xffffffffu, dl, 0), d1 = __shfl_sync(0xffffffffu, dl, 1),
+               d2 = __shfl_sync(0xffffffffu, dl, 2), d3 = __shfl_sync(0xffffffffu, dl, 3),
+               d4 = __shfl_sync(0xffffffffu, dl, 4), d5 = __shfl_sync(0xffffffffu, dl, 5);
+  const double* pc = d.pose[par] + (size_t)f * 8;
+  double q[4] = {pc[0], pc[1], pc[2], pc[3]};
+  double qn[4];
+  quat_plus(q, d0, d1, d2, qn);
+  t[0] = pc[4] + d3;
+  t[1] = pc[5] + d4;
+  t[2] = pc[6] + d5;
+  if (is_a && lane < 7) {
+    double* pn = d.pose[par ^ 1] + (size_t)f * 8;
+    const double val = lane == 0 ? qn[0] : lane == 1 ? qn[1] : lane == 2 ? qn[2] : lane == 3 ? qn[3]
+                     : lane == 4 ? t[0] : lane == 5 ? t[1] : t[2];
+    pn[lane] = val;
+  }
+  quat_to_rot(qn, R);
+}
+
+__global__ void __launch_bounds__(kRigWarps * 32, 1)
+k_rig_sweep(RigDev d, double huber_a, double* __restrict__ res_out, double* __restrict__ cost_out) {
+  __shared__ double s_cam[kMaxCams][12];                     // candidate camera R (9) t (3)
+  __shared__ double s_du[kMaxN6];
+  __shared__ double s_acc[kRigWarps / 2][kMaxCams][27];      // per pair: U_cc 21 (warp A) | g_c 6 (warp B)
+  __shared__ double s_sc[kRigWarps / 2][8];                  // per pair scalars
+  __shared__ int s_meta[2];
+  const WorkItem it = d.items[blockIdx.x];
+  RigState& ps = d.ps[0];
+  const int C = d.n_cams, n6 = 6 * C;
+  if (threadIdx.x == 0) {
+    s_meta[0] = ps.lm.par;
+    s_meta[1] = (ps.lm.status == 0 && ps.lm.solve_ok) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_meta[1] && !cost_out) return;
+  const int par = s_meta[0];
+  // cost_out != NULL: final per-observation cost pass at the CURRENT point (no step)
+  const int src = cost_out ? par : par ^ 1;
+  if (threadIdx.x < C) {
+    double q[4] = {ps.cam[src][threadIdx.x][0], ps.cam[src][threadIdx.x][1], ps.cam[src][threadIdx.x][2],
+                   ps.cam[src][threadIdx.x][3]};
+    double R[9];
+    quat_to_rot(q, R);
+    for (int i = 0; i < 9; ++i) s_cam[threadIdx.x][i] = R[i];
+    for (int i = 0; i < 3; ++i) s_cam[threadIdx.x][9 + i] = ps.cam[src][threadIdx.x][4 + i];
+  }
+  if (threadIdx.x < n6) s_du[threadIdx.x] = cost_out ? 0.0 : ps.du[threadIdx.x];
+  for (int i = threadIdx.x; i < (kRigWarps / 2) * kMaxCams * 27; i += blockDim.x) (&s_acc[0][0][0])[i] = 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1;
+  const bool is_a = (warp & 1) == 0;
+  double rho_sum = 0.0, sumsq = 0.0, nobs = 0.0, gTd = 0.0, dDd = 0.0;
+
+  for (int64_t f = it.v0 + pair; f < it.v1; f += kRigWarps / 2) {
+    double Rf[9], tf[3];
+    if (cost_out) {
+      const double* pc = d.pose[par] + (size_t)f * 8;
+      double q[4] = {pc[0], pc[1], pc[2], pc[3]};
+      quat_to_rot(q, Rf);
+      tf[0] = pc[4]; tf[1] = pc[5]; tf[2] = pc[6];
+    } else {
+      frame_prologue(d, par, f, lane, is_a, s_du, n6, Rf, tf, gTd, dDd);
+    }
+    double* blk = d.blk[par ^ 1] + (size_t)f * d.blk_stride;
+    double accf[21];  // warp A: V_f ; warp B: g_f in accf[0..5]
+#pragma unroll
+    for (int i = 0; i < 21; ++i) accf[i] = 0.0;
+    for (int c = 0; c < C; ++c) {
+      double Rc[9], tc[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rc[i] = s_cam[c][i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tc[i] = s_cam[c][9 + i];
+      const int64_t o0 = d.seg_off[f * C + c], o1 = d.seg_off[f * C + c + 1];
+      double acc[42];  // warp A: U_cc in acc[0..20] ; warp B: W_fc 36 | g_c 6
+#pragma unroll
+      for (int i = 0; i < 42; ++i) acc[i] = 0.0;
+      for (int64_t o = o0 + lane; o < o1; o += 32) {
+        const int ip = __ldg(d.pt + o);
+        const float mu = __ldg(d.u + o), mv = __ldg(d.v + o);
+        const float Xf = __ldg(d.Xw + 3 * (size_t)ip), Yf = __ldg(d.Xw + 3 * (size_t)ip + 1),
+                    Zf = __ldg(d.Xw + 3 * (size_t)ip + 2);
+        RigGeom g;
+        rig_geometry(Rf, tf, Rc, tc, (double)Xf, (double)Yf, (double)Zf, (double)mu, (double)mv, huber_a, g);
+        if (cost_out) {
+          if (is_a) cost_out[o] = 0.5 * g.rho;
+          continue;
+        }
+        if (is_a) {
+          if (res_out) {
+            res_out[2 * o] = g.ru;
+            res_out[2 * o + 1] = g.rv;
+          }
+          int idx = 0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b) {
+              accf[idx] = fma(g.jfu[a], g.jfu[b], fma(g.jfv[a], g.jfv[b], accf[idx]));
+              acc[idx] = fma(g.jcu[a], g.jcu[b], fma(g.jcv[a], g.jcv[b], acc[idx]));
+              ++idx;
+            }
+          rho_sum += g.rho;
+          sumsq += g.s;
+          nobs += 1.0;
+        } else {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+#pragma unroll
+            for (int b = 0; b < 6; ++b)
+              acc[a * 6 + b] = fma(g.jfu[a], g.jcu[b], fma(g.jfv[a], g.jcv[b], acc[a * 6 + b]));
+            accf[a] = fma(g.jfu[a], g.ru, fma(g.jfv[a], g.rv, accf[a]));
+            acc[36 + a] = fma(g.jcu[a], g.ru, fma(g.jcv[a], g.rv, acc[36 + a]));
+          }
+        }
+      }
+      if (cost_out) continue;
+      if (is_a) {
+        double tmp[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tmp[i] = i < 21 ? acc[i] : 0.0;
+        const double r = warp_reduce32(tmp, lane);
+        if (lane < 21) s_acc[pair][c][lane] += r;
+      } else {
+        double out[2];
+        warp_reduce_array<42>(acc, lane, out);
+        // element e = a*6+b of W_fc -> blk[27 + a*n6 + 6c + b]
+        {
+          const int a = lane / 6, b = lane - 6 * a;
+          blk[27 + a * n6 + 6 * c + b] = out[0];
+        }
+        if (lane < 4) {
+          const int e = 32 + lane, a = e / 6, b = e - 6 * a;
+          blk[27 + a * n6 + 6 * c + b] = out[1];
+        } else if (lane < 10) {
+          s_acc[pair][c][21 + lane - 4] += out[1];
+        }
+      }
+    }
+    if (cost_out) continue;
+    {
+      double tmp[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tmp[i] = i < 21 ? accf[i] : 0.0;
+      const double r = warp_reduce32(tmp, lane);
+      if (is_a) {
+        if (lane < 21) blk[lane] = r;
+      } else {
+        if (lane < 6) blk[21 + lane] = r;
+      }
+    }
+  }
+  if (cost_out) return;
+  if (is_a) {
+    double tmp[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tmp[i] = 0.0;
+    tmp[0] = rho_sum; tmp[1] = sumsq; tmp[2] = gTd; tmp[3] = dDd; tmp[4] = nobs;
+    const double r = warp_reduce32(tmp, lane);
+    if (lane < 8) s_sc[pair][lane] = lane < 5 ? r : 0.0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < kRigPart; c += blockDim.x) {
+    double s = 0.0;
+    if (c < 27 * kMaxCams) {
+      const int cam = c / 27, e = c - 27 * cam;
+      if (cam < C)
+        for (int p = 0; p < kRigWarps / 2; ++p) s += s_acc[p][cam][e];
+    } else if (c < 27 * kMaxCams + 5) {
+      for (int p = 0; p < kRigWarps / 2; ++p) s += s_sc[p][c - 27 * kMaxCams];
+    }
+    d.sweep_part[(size_t)blockIdx.x * kRigPart + c] = s;
+  }
+}
+
+// --------------------------------------------------------------------------
+// frame elimination, one warp per frame, lane j = column j of [W | g_f]
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRigSchurWarps * 32) k_rig_schur(RigDev d, LmParams P) {
+  __shared__ double s_part[kRigSchurWarps][kRigSchurPart];
+  __shared__ int s_meta[2];
+  __shared__ double s_lambda;
+  const WorkItem it = d.items[blockIdx.x];
+  RigState& ps = d.ps[0];
+  const int C = d.n_cams, n6 = 6 * C;
+  if (threadIdx.x == 0) {
+    s_meta[0] = ps.lm.par;
+    s_meta[1] = (ps.lm.status == 0 || ps.lm.finalize) ? 1 : 0;
+    s_lambda = ps.lm.lambda;
+  }
+  __syncthreads();
+  if (!s_meta[1]) return;
+  const int par = s_meta[0];
+  const double lambda = s_lambda;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double acc[kMaxN6];
+#pragma unroll
+  for (int j = 0; j < kMaxN6; ++j) acc[j] = 0.0;
+  double gDg = 0.0, fails = 0.0;
+  for (int64_t f = it.v0 + warp; f < it.v1; f += kRigSchurWarps) {
+    const double* blk = d.blk[par] + (size_t)f * d.blk_stride;
+    double A[6][6], Dv[6], gv[6];
+    {
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) {
+          A[b][a] = blk[idx];
+          ++idx;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      gv[a] = blk[21 + a];
+      Dv[a] = clampd(A[a][a], P.min_diagonal, P.max_diagonal);
+      if (lane == 0 && A[a][a] > 0.0) gDg += gv[a] * gv[a] / A[a][a];
+      A[a][a] += lambda * Dv[a];
+    }
+    const bool ok = chol6(A);
+    if (!ok && lane == 0) fails += 1.0;
+    double col[6], y[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double w = 0.0;
+      if (lane < n6) w = blk[27 + a * n6 + lane];
+      else if (lane == n6) w = gv[a];
+      col[a] = w;
+      y[a] = w;
+    }
+    chol6_solve(A, y);
+    double* yz = d.yz + (size_t)f * d.yz_stride;
+    if (lane < n6) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) yz[a * n6 + lane] = y[a];
+    } else if (lane == n6) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        yz[6 * n6 + a] = y[a];
+        yz[6 * n6 + 6 + a] = gv[a];
+        yz[6 * n6 + 12 + a] = Dv[a];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxN6; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s = fma(__shfl_sync(0xffffffffu, col[a], j), y[a], s);
+      if (j < n6) acc[j] += s;
+    }
+  }
+  if (lane <= n6) {
+#pragma unroll
+    for (int j = 0; j < kMaxN6; ++j) s_part[warp][lane * kMaxN6 + j] = acc[j];
+  }
+  if (lane == 0) {
+    s_part[warp][kRigSchurPart - 2] = gDg;
+    s_part[warp][kRigSchurPart - 1] = fails;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < kRigSchurPart; c += blockDim.x) {
+    const int k = c / kMaxN6;
+    double s = 0.0;
+    if (k <= n6 || c >= kRigSchurPart - 2)
+      for (int w = 0; w < kRigSchurWarps; ++w) s += s_part[w][c];
+    d.schur_part[(size_t)blockIdx.x * kRigSchurPart + c] = s;
+  }
+}
+
+// fixed-order sum of the item partials: block b owns components [32b, 32b+32), thread
+// (c, seg) sums items seg, seg+8, ... and the 8 segment sums are combined in order
+__global__ void __launch_bounds__(256) k_rig_reduce(const double* __restrict__ part, int stride, int n_items,
+                                                    double* __restrict__ red) {
+  __shared__ double s_buf[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), seg = threadIdx.x >> 5;
+  double s = 0.0;
+  if (c < stride)
+    for (int i = seg; i < n_items; i += 8) s += part[(size_t)i * stride + c];
+  s_buf[seg][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (seg == 0 && c < stride) {
+    double tot = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) tot += s_buf[g][threadIdx.x];
+    red[c] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_rig_decide(RigDev d, LmParams P) {
+  __shared__ double s_buf[kRigPart];
+  RigState& ps = d.ps[0];
+  if (ps.lm.status != 0) return;
+  const bool evaluated = ps.lm.solve_ok != 0;
+  if (evaluated) {
+    for (int c = threadIdx.x; c < kRigPart; c += blockDim.x) s_buf[c] = d.red_sweep[c];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  LmState& s = ps.lm;
+  if (!evaluated) {
+    lm_reject(s, P, d.n_done);
+    s.solve_ok = 1;
+    if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, d.n_done, true);
+    return;
+  }
+  const double* r = s_buf;
+  const int base = 27 * kMaxCams;
+  const bool accept = lm_decide(s, P, 0.5 * r[base], r[base + 2] + s.gTd_u, r[base + 3] + s.dDd_u, d.n_done);
+  if (accept) {
+    for (int c = 0; c < ps.n_cams; ++c) {
+      for (int e = 0; e < 21; ++e) ps.Ucc[c][e] = r[27 * c + e];
+      for (int e = 0; e < 6; ++e) ps.gc[c][e] = r[27 * c + 21 + e];
+    }
+    s.sumsq = r[base + 1];
+    s.n_obs = r[base + 4];
+  }
+}
+
+// reduced (6C x 6C) solve, block-cooperative Cholesky in shared memory
+__global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
+  __shared__ double s_buf[kRigSchurPart];
+  __shared__ double S[kMaxN6 * kMaxN6];
+  __shared__ double rhs[kMaxN6], Du[kMaxN6];
+  __shared__ int s_flag[2];
+  RigState& ps = d.ps[0];
+  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
+  for (int c = threadIdx.x; c < kRigSchurPart; c += blockDim.x) s_buf[c] = d.red_schur[c];
+  __syncthreads();
+  LmState& s = ps.lm;
+  const int C = ps.n_cams, n = 6 * C, par = s.par;
+  const double* r = s_buf;
+  if (threadIdx.x == 0) {
+    double gDg = r[kRigSchurPart - 2];
+    for (int c = 0; c < C; ++c) {
+      if (ps.frozen[c]) continue;
+      int idx = 0;
+      for (int a = 0; a < 6; ++a) {
+        const double dd = ps.Ucc[c][idx];
+        if (dd > 0.0) gDg += ps.gc[c][a] * ps.gc[c][a] / dd;
+        idx += 6 - a;
+      }
+    }
+    const double rnorm = sqrt(2.0 * s.cost);
+    s.grad_norm = rnorm > 0.0 ? sqrt(gDg) / rnorm : 0.0;
+    int go = 1;
+    if (s.finalize) {
+      s.finalize = 0;
+      go = 0;
+    } else if (s.cost == 0.0 || sqrt(gDg) <= P.gradient_tolerance * rnorm) {
+      lm_finish(s, 1, d.n_done, false);
+      go = 0;
+    } else {
+      s.iterations++;
+      if (r[kRigSchurPart - 1] > 0.0) {
+        s.solve_ok = 0;
+        go = 0;
+      }
+    }
+    s_flag[0] = go;
+    s_flag[1] = 1;
+  }
+  __syncthreads();
+  if (!s_flag[0]) return;
+  const double lambda = s.lambda;
+  // assemble S = U + lambda D - W'Y (upper from the partial, symmetrised), rhs = -g + W'z
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int a = e / n, b = e - n * a;
+    const int lo = a <= b ? a : b, hi = a <= b ? b : a;
+    double val = -r[hi * kMaxN6 + lo];  // (W'Y)[lo][hi] lives in column hi, row lo
+    const int ca = a / 6, cb = b / 6;
+    if (ca == cb) {
+      const int i = lo - 6 * ca, j = hi - 6 * ca;
+      val += ps.Ucc[ca][i * 6 - i * (i - 1) / 2 + (j - i)];
+    }
+    S[a * n + b] = val;
+  }
+  __syncthreads();
+  for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    const int c = a / 6, i = a - 6 * c;
+    const double dd = ps.Ucc[c][i * 6 - i * (i - 1) / 2];
+    Du[a] = clampd(dd, P.min_diagonal, P.max_diagonal);
+    rhs[a] = -ps.gc[c][i] + r[n * kMaxN6 + a];
+    S[a * n + a] += lambda * Du[a];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int a = e / n, b = e - n * a;
+    if (ps.frozen[a / 6] || ps.frozen[b / 6]) S[e] = (a == b) ? 1.0 : 0.0;
+  }
+  for (int a = threadIdx.x; a < n; a += blockDim.x)
+    if (ps.frozen[a / 6]) rhs[a] = 0.0;
+  __syncthreads();
+  // right-looking Cholesky, lower triangle, all threads
+  for (int j = 0; j < n; ++j) {
+    if (threadIdx.x == 0) {
+      const double dd = S[j * n + j];
+      if (!(dd > 0.0) || !isfinite(dd)) s_flag[1] = 0;
+      S[j * n + j] = sqrt(dd);
+    }
+    __syncthreads();
+    if (!s_flag[1]) break;
+    const double inv = 1.0 / S[j * n + j];
+    for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) S[i * n + j] *= inv;
+    __syncthreads();
+    const int m = n - j - 1;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+      const int i = j + 1 + e / m, k = j + 1 + e % m;
+      if (k <= i) S[i * n + k] -= S[i * n + j] * S[k * n + j];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  if (!s_flag[1]) {
+    s.solve_ok = 0;
+    return;
+  }
+  for (int i = 0; i < n; ++i) {
+    double acc = rhs[i];
+    for (int k = 0; k < i; ++k) acc -= S[i * n + k] * rhs[k];
+    rhs[i] = acc / S[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double acc = rhs[i];
+    for (int k = i + 1; k < n; ++k) acc -= S[k * n + i] * rhs[k];
+    rhs[i] = acc / S[i * n + i];
+  }
+  double gTd = 0.0, dDd = 0.0;
+  for (int c = 0; c < C; ++c) {
+    double dc[6];
+    for (int i = 0; i < 6; ++i) {
+      dc[i] = ps.frozen[c] ? 0.0 : rhs[6 * c + i];
+      ps.du[6 * c + i] = dc[i];
+      gTd += ps.gc[c][i] * dc[i];
+      dDd += dc[i] * dc[i] * Du[6 * c + i];
+    }
+    double q[4] = {ps.cam[par][c][0], ps.cam[par][c][1], ps.cam[par][c][2], ps.cam[par][c][3]};
+    double qn[4];
+    quat_plus(q, dc[0], dc[1], dc[2], qn);
+    for (int i = 0; i < 4; ++i) ps.cam[par ^ 1][c][i] = qn[i];
+    for (int i = 0; i < 3; ++i) ps.cam[par ^ 1][c][4 + i] = ps.cam[par][c][4 + i] + dc[3 + i];
+  }
+  s.gTd_u = gTd;
+  s.dDd_u = dDd;
+  s.solve_ok = 1;
+}
+
+__global__ void k_rig_init_state(RigDev d, LmParams P, const double* cam0, const int* frozen, int n_items,
+                                 double meas_scale) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  RigState& ps = d.ps[0];
+  lm_init(ps.lm, P);
+  ps.lm.meas_scale = meas_scale;
+  ps.n_cams = d.n_cams;
+  ps.item0 = 0;
+  ps.item1 = n_items;
+  for (int c = 0; c < kMaxCams; ++c) {
+    for (int k = 0; k < 8; ++k) {
+      const double v = c < d.n_cams ? cam0[c * 8 + k] : 0.0;
+      ps.cam[0][c][k] = v;
+      ps.cam[1][c][k] = v;
+    }
+    ps.frozen[c] = c < d.n_cams ? frozen[c] : 1;
+    for (int e = 0; e < 21; ++e) ps.Ucc[c][e] = 0.0;
+    for (int e = 0; e < 6; ++e) ps.gc[c][e] = 0.0;
+  }
+  for (int k = 0; k < kMaxN6; ++k) ps.du[k] = 0.0;
+  *d.n_done = 0;
+}
+
+}  // namespace ccg
+
+// ==========================================================================
+// host side
+// ==========================================================================
+using namespace ccg;
+
+struct ccg_rig_problem {
+  ccg_ctx* ctx = nullptr;
+  int64_t n_frames = 0, n_obs = 0, n_points = 0;
+  int n_cams = 0, n_items = 0, shared = 0;
+  RigDev dev;
+  std::vector<void*> allocs;
+  double *d_cam0 = nullptr, *d_pose0 = nullptr;
+  int* d_frozen = nullptr;
+  std::vector<int64_t> perm;  // sorted position -> caller's observation index
+  double meas_scale = 0.0;
+  double huber_a = (double)(3.0f / 500.0f);  // of the last run (final per-observation cost pass)
+};
+
+namespace {
+
+#define CCG_TRY(x)                   \
+  do {                               \
+    const int rc__ = (x);            \
+    if (rc__ != CCG_OK) return rc__; \
+  } while (0)
+
+template <typename T>
+int rig_alloc(ccg_rig_problem* p, T** out, size_t n) {
+  void* ptr = nullptr;
+  cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return set_error(p->ctx, CCG_ERR_CUDA, "cudaMalloc", e);
+  p->allocs.push_back(ptr);
+  *out = (T*)ptr;
+  return CCG_OK;
+}
+
+void rig_free(ccg_rig_problem* p) {
+  if (!p) return;
+  if (p->ctx) cudaSetDevice(p->ctx->device);
+  for (void* a : p->allocs) cudaFree(a);
+  delete p;
+}
+
+int rig_build(ccg_ctx* ctx, const float* u, const float* v, const int32_t* obs_cam, const int64_t* obs_point,
+              const int64_t* frame_offsets, int64_t n_frames, const float* Xw, int64_t n_points,
+              int32_t n_cams, const double* q_c, const double* t_c, const uint8_t* cam_frozen,
+              const double* q_f, const double* t_f, int shared, ccg_rig_problem* p) {
+  p->ctx = ctx;
+  p->n_frames = n_frames;
+  p->n_cams = n_cams;
+  p->n_points = n_points;
+  p->shared = shared;
+  const int C = n_cams;
+  const int64_t o0 = frame_offsets[0], n_obs = frame_offsets[n_frames] - o0;
+  p->n_obs = n_obs;
+  // ---- stable sort of every frame's observations by camera -> contiguous (frame, camera) segments
+  std::vector<int64_t> seg((size_t)n_frames * C + 1, 0);
+  p->perm.resize((size_t)n_obs);
+  std::vector<float> su((size_t)n_obs), sv((size_t)n_obs);
+  std::vector<int> spt((size_t)n_obs);
+  float mscale = 0.0f;
+  int64_t w = 0;
+  for (int64_t f = 0; f < n_frames; ++f) {
+    for (int c = 0; c < C; ++c) {
+      seg[(size_t)f * C + c] = w;
+      for (int64_t o = frame_offsets[f]; o < frame_offsets[f + 1]; ++o) {
+        if (obs_cam[o] != c) continue;
+        p->perm[(size_t)w] = o - o0;
+        su[(size_t)w] = u[o];
+        sv[(size_t)w] = v[o];
+        spt[(size_t)w] = (int)obs_point[o];
+        mscale = std::max(mscale, std::max(std::fabs(u[o]), std::fabs(v[o])));
+        ++w;
+      }
+    }
+  }
+  seg[(size_t)n_frames * C] = w;
+  if (w != n_obs) return set_error(ctx, CCG_ERR_BAD_ARG, "camera id out of range");
+  p->meas_scale = (double)mscale;
+
+  // ---- work items over frames
+  const int64_t target = (int64_t)ctx->sm_count * 4;
+  const int64_t fpi = std::max<int64_t>(kRigWarps / 2, (n_frames + target - 1) / std::max<int64_t>(target, 1));
+  std::vector<WorkItem> items;
+  const int64_t n_it = std::max<int64_t>(1, (n_frames + fpi - 1) / fpi);
+  for (int64_t i = 0; i < n_it; ++i) {
+    WorkItem it;
+    it.problem = 0;
+    it.v0 = (int)(n_frames * i / n_it);
+    it.v1 = (int)(n_frames * (i + 1) / n_it);
+    it.pad = 0;
+    items.push_back(it);
+  }
+  p->n_items = (int)items.size();
+
+  RigDev& d = p->dev;
+  std::memset(&d, 0, sizeof(d));
+  d.n_cams = C;
+  d.blk_stride = ((27 + 36 * C) + 3) / 4 * 4;
+  d.yz_stride = ((36 * C + 18) + 3) / 4 * 4;
+  float *du_ = nullptr, *dv_ = nullptr, *dX = nullptr;
+  int* dpt = nullptr;
+  int64_t* dseg = nullptr;
+  WorkItem* ditems = nullptr;
+  CCG_TRY(rig_alloc(p, &du_, (size_t)n_obs));
+  CCG_TRY(rig_alloc(p, &dv_, (size_t)n_obs));
+  CCG_TRY(rig_alloc(p, &dpt, (size_t)n_obs));
+  CCG_TRY(rig_alloc(p, &dX, (size_t)n_points * 3));
+  CCG_TRY(rig_alloc(p, &dseg, seg.size()));
+  CCG_TRY(rig_alloc(p, &ditems, items.size()));
+  CCG_TRY(rig_alloc(p, &d.pose[0], (size_t)n_frames * 8));
+  CCG_TRY(rig_alloc(p, &d.pose[1], (size_t)n_frames * 8));
+  CCG_TRY(rig_alloc(p, &p->d_pose0, (size_t)n_frames * 8));
+  CCG_TRY(rig_alloc(p, &d.blk[0], (size_t)n_frames * d.blk_stride));
+  CCG_TRY(rig_alloc(p, &d.blk[1], (size_t)n_frames * d.blk_stride));
+  CCG_TRY(rig_alloc(p, &d.yz, (size_t)n_frames * d.yz_stride));
+  CCG_TRY(rig_alloc(p, &d.sweep_part, items.size() * kRigPart));
+  CCG_TRY(rig_alloc(p, &d.schur_part, items.size() * kRigSchurPart));
+  CCG_TRY(rig_alloc(p, &d.red_sweep, (size_t)kRigPart));
+  CCG_TRY(rig_alloc(p, &d.red_schur, (size_t)kRigSchurPart));
+  CCG_TRY(rig_alloc(p, &d.ps, (size_t)1));
+  CCG_TRY(rig_alloc(p, &d.n_done, (size_t)1));
+  CCG_TRY(rig_alloc(p, &p->d_cam0, (size_t)kMaxCams * 8));
+  CCG_TRY(rig_alloc(p, &p->d_frozen, (size_t)kMaxCams));
+  d.u = du_;
+  d.v = dv_;
+  d.pt = dpt;
+  d.Xw = dX;
+  d.seg_off = dseg;
+  d.items = ditems;
+  cudaStream_t st = ctx->stream;
+  std::vector<double> pose((size_t)n_frames * 8, 0.0), cam((size_t)kMaxCams * 8, 0.0);
+  for (int64_t f = 0; f < n_frames; ++f) {
+    for (int k = 0; k < 4; ++k) pose[(size_t)f * 8 + k] = q_f[f * 4 + k];
+    for (int k = 0; k < 3; ++k) pose[(size_t)f * 8 + 4 + k] = t_f[f * 3 + k];
+  }
+  std::vector<int> frozen(kMaxCams, 1);
+  for (int c = 0; c < C; ++c) {
+    for (int k = 0; k < 4; ++k) cam[(size_t)c * 8 + k] = q_c[c * 4 + k];
+    for (int k = 0; k < 3; ++k) cam[(size_t)c * 8 + 4 + k] = t_c[c * 3 + k];
+    frozen[c] = cam_frozen && cam_frozen[c] ? 1 : 0;
+  }
+  CCG_CUDA(ctx, cudaMemcpyAsync(du_, su.data(), sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(dv_, sv.data(), sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(dpt, spt.data(), sizeof(int) * n_obs, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(dX, Xw, sizeof(float) * 3 * n_points, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(dseg, seg.data(), sizeof(int64_t) * seg.size(), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(ditems, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_pose0, pose.data(), sizeof(double) * pose.size(), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_cam0, cam.data(), sizeof(double) * cam.size(), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_frozen, frozen.data(), sizeof(int) * kMaxCams, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaStreamSynchronize(st));
+  return CCG_OK;
+}
+
+int rig_reset(ccg_rig_problem* p, const LmParams& P) {
+  ccg_ctx* ctx = p->ctx;
+  RigDev& d = p->dev;
+  CCG_CUDA(ctx, cudaMemcpyAsync(d.pose[0], p->d_pose0, sizeof(double) * p->n_frames * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CCG_CUDA(ctx, cudaMemsetAsync(d.yz, 0, sizeof(double) * std::max<int64_t>(p->n_frames, 1) * d.yz_stride, ctx->stream));
+  k_rig_init_state<<<1, 32, 0, ctx->stream>>>(d, P, p->d_cam0, p->d_frozen, p->n_items, p->meas_scale);
+  ctx->launches++;
+  CCG_CUDA(ctx, cudaGetLastError());
+  return CCG_OK;
+}
+
+enum { TAG_SWEEP = 0, TAG_SCHUR = 1, TAG_SMALL = 2 };
+
+int rig_sweep_decide(ccg_rig_problem* p, const LmParams& P, Profiler& prof, double* res_out, int* nar) {
+  ccg_ctx* ctx = p->ctx;
+  RigDev& d = p->dev;
+  cudaStream_t st = ctx->stream;
+  prof.begin(TAG_SWEEP);
+  k_rig_sweep<<<p->n_items, kRigWarps * 32, 0, st>>>(d, P.huber_a, res_out, nullptr);
+  prof.end();
+  ctx->launches++;
+  prof.begin(TAG_SMALL);
+  k_rig_reduce<<<(kRigPart + 31) / 32, 256, 0, st>>>(d.sweep_part, kRigPart, p->n_items, d.red_sweep);
+  if (p->shared && ctx->world > 1) {
+    CCG_TRY(nccl_allreduce_sum(ctx, d.red_sweep, kRigPart));
+    (*nar)++;
+  }
+  k_rig_decide<<<1, 256, 0, st>>>(d, P);
+  ctx->launches += 2;
+  prof.end();
+  return CCG_OK;
+}
+
+int rig_schur_solve(ccg_rig_problem* p, const LmParams& P, Profiler& prof, int* nar) {
+  ccg_ctx* ctx = p->ctx;
+  RigDev& d = p->dev;
+  cudaStream_t st = ctx->stream;
+  prof.begin(TAG_SCHUR);
+  k_rig_schur<<<p->n_items, kRigSchurWarps * 32, 0, st>>>(d, P);
+  prof.end();
+  ctx->launches++;
+  prof.begin(TAG_SMALL);
+  k_rig_reduce<<<(kRigSchurPart + 31) / 32, 256, 0, st>>>(d.schur_part, kRigSchurPart, p->n_items, d.red_schur);
+  if (p->shared && ctx->world > 1) {
+    CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, kRigSchurPart));
+    (*nar)++;
+  }
+  k_rig_solve<<<1, 256, 0, st>>>(d, P);
+  ctx->launches += 2;
+  prof.end();
+  return CCG_OK;
+}
+
+int rig_run(ccg_rig_problem* p, const ccg_opts& opts, ccg_timing* timing) {
+  ccg_ctx* ctx = p->ctx;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const LmParams P = to_params(opts);
+  Profiler prof;
+  prof.ctx = ctx;
+  prof.on = opts.profile != 0;
+  Profiler tot;
+  tot.ctx = ctx;
+  const size_t e0 = tot.grab(), e1 = tot.grab();
+  prof.used = tot.used;
+  int nar = 0;
+  cudaEventRecord(ctx->events[e0], ctx->stream);
+  CCG_TRY(rig_reset(p, P));
+  CCG_TRY(rig_sweep_decide(p, P, prof, nullptr, &nar));
+  int done = 0;
+  for (int it = 0; it <= opts.max_iterations * 2 + 64; ++it) {
+    CCG_TRY(rig_schur_solve(p, P, prof, &nar));
+    if (done >= 1) break;
+    CCG_TRY(rig_sweep_decide(p, P, prof, nullptr, &nar));
+    if ((it & 3) == 3) {
+      CCG_CUDA(ctx, cudaMemcpyAsync(ctx->h_poll, p->dev.n_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      done = ctx->h_poll[0];
+    }
+  }
+  cudaEventRecord(ctx->events[e1], ctx->stream);
+  CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  CCG_CUDA(ctx, cudaGetLastError());
+  if (timing) {
+    std::memset(timing, 0, sizeof(*timing));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->events[e0], ctx->events[e1]);
+    timing->total_ms = ms;
+    double tms[4];
+    int tn[4];
+    prof.collect(tms, tn);
+    timing->sweep_ms = tms[TAG_SWEEP];
+    timing->schur_ms = tms[TAG_SCHUR];
+    timing->small_ms = tms[TAG_SMALL];
+    timing->sweep_launches = tn[TAG_SWEEP];
+    timing->schur_launches = tn[TAG_SCHUR];
+    timing->small_launches = tn[TAG_SMALL];
+    timing->allreduces = nar;
+    timing->sweep_obs = p->n_obs;
+    timing->sweep_views = p->n_frames;
+  }
+  return CCG_OK;
+}
+
+int rig_download(ccg_rig_problem* p, double* q_c, double* t_c, double* q_f, double* t_f, double* obs_cost,
+                 ccg_report* report) {
+  ccg_ctx* ctx = p->ctx;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  RigState st;
+  CCG_CUDA(ctx, cudaMemcpy(&st, p->dev.ps, sizeof(RigState), cudaMemcpyDeviceToHost));
+  const int par = st.lm.par;
+  for (int c = 0; c < p->n_cams; ++c) {
+    if (q_c) for (int k = 0; k < 4; ++k) q_c[c * 4 + k] = st.cam[par][c][k];
+    if (t_c) for (int k = 0; k < 3; ++k) t_c[c * 3 + k] = st.cam[par][c][4 + k];
+  }
+  if (q_f || t_f) {
+    std::vector<double> pose((size_t)p->n_frames * 8);
+    CCG_CUDA(ctx, cudaMemcpy(pose.data(), p->dev.pose[par], sizeof(double) * pose.size(), cudaMemcpyDeviceToHost));
+    for (int64_t f = 0; f < p->n_frames; ++f) {
+      if (q_f) for (int k = 0; k < 4; ++k) q_f[f * 4 + k] = pose[(size_t)f * 8 + k];
+      if (t_f) for (int k = 0; k < 3; ++k) t_f[f * 3 + k] = pose[(size_t)f * 8 + 4 + k];
+    }
+  }
+  if (obs_cost && p->n_obs > 0) {
+    // per-observation 0.5*rho at the returned point (extrinsics_calibrator.cpp:219-225)
+    double* d_cost = nullptr;
+    CCG_CUDA(ctx, cudaMalloc(&d_cost, sizeof(double) * p->n_obs));
+    k_rig_sweep<<<p->n_items, kRigWarps * 32, 0, ctx->stream>>>(p->dev, p->huber_a, nullptr, d_cost);
+    ctx->launches++;
+    std::vector<double> sorted((size_t)p->n_obs);
+    cudaError_t e = cudaMemcpyAsync(sorted.data(), d_cost, sizeof(double) * p->n_obs, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_cost);
+    if (e != cudaSuccess) return set_error(ctx, CCG_ERR_CUDA, "obs cost", e);
+    for (int64_t i = 0; i < p->n_obs; ++i) obs_cost[p->perm[(size_t)i]] = sorted[(size_t)i];
+  }
+  if (report) {
+    report->iterations = st.lm.iterations;
+    report->accepted = st.lm.accepted;
+    report->rejected = st.lm.rejected;
+    report->sweeps = st.lm.sweeps;
+    report->termination = st.lm.status;
+    report->pad_ = 0;
+    report->initial_cost = st.lm.cost0;
+    report->final_cost = st.lm.cost;
+    report->gradient_norm = st.lm.grad_norm;
+    report->rms = st.lm.n_obs > 0.0 ? std::sqrt(st.lm.sumsq / st.lm.n_obs) : 0.0;
+  }
+  return st.lm.status < 0 ? st.lm.status : CCG_OK;
+}
+
+bool rig_bad(const float* u, const float* v, const int32_t* obs_cam, const int64_t* obs_point,
+             const int64_t* frame_offsets, int64_t n_frames, const float* Xw, int64_t n_points, int n_cams) {
+  if (!frame_offsets || n_frames < 0 || n_cams < 1 || n_points < 0) return true;
+  const int64_t n = frame_offsets[n_frames] - frame_offsets[0];
+  if (n < 0 || (n > 0 && (!u || !v || !obs_cam || !obs_point || !Xw))) return true;
+  for (int64_t f = 0; f < n_frames; ++f)
+    if (frame_offsets[f + 1] < frame_offsets[f]) return true;
+  for (int64_t o = frame_offsets[0]; o < frame_offsets[n_frames]; ++o)
+    if (obs_cam[o] < 0 || obs_cam[o] >= n_cams || obs_point[o] < 0 || obs_point[o] >= n_points) return true;
+  return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccg_rig_create(ccg_ctx* ctx, const float* u, const float* v, const int32_t* obs_cam,
+                   const int64_t* obs_point, const int64_t* frame_offsets, int64_t n_frames,
+                   const float* Xw, int64_t n_points, int32_t n_cams, const double* q_c,
+                   const double* t_c, const uint8_t* cam_frozen, const double* q_f,
+                   const double* t_f, int shared, ccg_rig_problem** out) {
+  if (!ctx || !out) return CCG_ERR_BAD_ARG;
+  *out = nullptr;
+  if (rig_bad(u, v, obs_cam, obs_point, frame_offsets, n_frames, Xw, n_points, n_cams) || !q_c || !t_c ||
+      (n_frames > 0 && (!q_f || !t_f)))
+    return set_error(ctx, CCG_ERR_BAD_ARG, "ccg_rig_create: bad argument");
+  if (n_cams > kMaxCams) return set_error(ctx, CCG_ERR_UNSUPPORTED, "at most 5 cameras per rig in this build");
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  ccg_rig_problem* p = new ccg_rig_problem();
+  const int rc = rig_build(ctx, u, v, obs_cam, obs_point, frame_offsets, n_frames, Xw, n_points, n_cams, q_c,
+                           t_c, cam_frozen, q_f, t_f, shared, p);
+  if (rc != CCG_OK) {
+    rig_free(p);
+    return rc;
+  }
+  *out = p;
+  return CCG_OK;
+}
+
+int ccg_rig_reset(ccg_rig_problem* p) {
+  if (!p) return CCG_ERR_BAD_ARG;
+  ccg_opts o;
+  ccg_default_opts(&o);
+  CCG_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+  return rig_reset(p, to_params(o));
+}
+
+int ccg_rig_run(ccg_rig_problem* p, const ccg_opts* opts, ccg_timing* timing) {
+  if (!p) return CCG_ERR_BAD_ARG;
+  ccg_opts o;
+  if (opts) o = *opts; else { ccg_default_opts(&o); o.max_iterations = 1000; }
+  p->huber_a = o.huber_a;
+  return rig_run(p, o, timing);
+}
+
+int ccg_rig_download(ccg_rig_problem* p, double* q_c, double* t_c, double* q_f, double* t_f,
+                     double* obs_cost, ccg_report* report) {
+  if (!p) return CCG_ERR_BAD_ARG;
+  return rig_download(p, q_c, t_c, q_f, t_f, obs_cost, report);
+}
+
+void ccg_rig_destroy(ccg_rig_problem* p) { rig_free(p); }
+
+int ccg_rig_solve(ccg_ctx* ctx, const float* u, const float* v, const int32_t* obs_cam,
+                  const int64_t* obs_point, const int64_t* frame_offsets, int64_t n_frames,
+                  const float* Xw, int64_t n_points, int32_t n_cams, double* q_c, double* t_c,
+                  const uint8_t* cam_frozen, double* q_f, double* t_f, double* obs_cost,
+                  const ccg_opts* opts, ccg_report* report) {
+  ccg_rig_problem* p = nullptr;
+  int rc = ccg_rig_create(ctx, u, v, obs_cam, obs_point, frame_offsets, n_frames, Xw, n_points, n_cams, q_c,
+                          t_c, cam_frozen, q_f, t_f, 0, &p);
+  if (rc != CCG_OK) return rc;
+  rc = ccg_rig_run(p, opts, nullptr);
+  if (rc == CCG_OK) rc = rig_download(p, q_c, t_c, q_f, t_f, obs_cost, report);
+  rig_free(p);
+  return rc;
+}
+
+int ccg_rig_eval(ccg_ctx* ctx, const float* u, const float* v, const int32_t* obs_cam,
+                 const int64_t* obs_point, const int64_t* frame_offsets, int64_t n_frames,
+                 const float* Xw, int64_t n_points, int32_t n_cams, const double* q_c,
+                 const double* t_c, const double* q_f, const double* t_f, double huber_a,
+                 double* res, double* Vb, double* Wb, double* gvb, double* U, double* gu,
+                 double* cost) {
+  ccg_rig_problem* p = nullptr;
+  int rc = ccg_rig_create(ctx, u, v, obs_cam, obs_point, frame_offsets, n_frames, Xw, n_points, n_cams, q_c,
+                          t_c, nullptr, q_f, t_f, 0, &p);
+  if (rc != CCG_OK) return rc;
+  auto body = [&]() -> int {
+    ccg_opts o;
+    ccg_default_opts(&o);
+    o.huber_a = huber_a;
+    const LmParams P = to_params(o);
+    CCG_TRY(rig_reset(p, P));
+    double* d_res = nullptr;
+    if (res) CCG_TRY(rig_alloc(p, &d_res, (size_t)p->n_obs * 2));
+    Profiler prof;
+    prof.ctx = ctx;
+    int nar = 0;
+    CCG_TRY(rig_sweep_decide(p, P, prof, d_res, &nar));
+    CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CCG_CUDA(ctx, cudaGetLastError());
+    const int C = n_cams, n6 = 6 * C, bs = p->dev.blk_stride;
+    std::vector<double> blk((size_t)n_frames * bs);
+    CCG_CUDA(ctx, cudaMemcpy(blk.data(), p->dev.blk[1], sizeof(double) * blk.size(), cudaMemcpyDeviceToHost));
+    RigState st;
+    CCG_CUDA(ctx, cudaMemcpy(&st, p->dev.ps, sizeof(RigState), cudaMemcpyDeviceToHost));
+    if (res) {
+      std::vector<double> sorted((size_t)p->n_obs * 2);
+      CCG_CUDA(ctx, cudaMemcpy(sorted.data(), d_res, sizeof(double) * sorted.size(), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < p->n_obs; ++i) {
+        res[2 * p->perm[(size_t)i]] = sorted[(size_t)2 * i];
+        res[2 * p->perm[(size_t)i] + 1] = sorted[(size_t)2 * i + 1];
+      }
+    }
+    for (int64_t f = 0; f < n_frames; ++f) {
+      const double* b = &blk[(size_t)f * bs];
+      if (Vb) {
+        int idx = 0;
+        for (int a = 0; a < 6; ++a)
+          for (int c = a; c < 6; ++c) {
+            Vb[f * 36 + a * 6 + c] = b[idx];
+            Vb[f * 36 + c * 6 + a] = b[idx];
+            ++idx;
+          }
+      }
+      if (gvb) for (int a = 0; a < 6; ++a) gvb[f * 6 + a] = b[21 + a];
+      if (Wb) for (int e = 0; e < 6 * n6; ++e) Wb[f * 6 * n6 + e] = b[27 + e];
+    }
+    if (U) {
+      std::fill(U, U + (size_t)n6 * n6, 0.0);
+      for (int c = 0; c < C; ++c) {
+        int idx = 0;
+        for (int a = 0; a < 6; ++a)
+          for (int b2 = a; b2 < 6; ++b2) {
+            U[(size_t)(6 * c + a) * n6 + 6 * c + b2] = st.Ucc[c][idx];
+            U[(size_t)(6 * c + b2) * n6 + 6 * c + a] = st.Ucc[c][idx];
+            ++idx;
+          }
+      }
+    }
+    if (gu) for (int c = 0; c < C; ++c) for (int a = 0; a < 6; ++a) gu[6 * c + a] = st.gc[c][a];
+    if (cost) *cost = st.lm.cost;
+    return CCG_OK;
+  };
+  rc = body();
+  rig_free(p);
+  return rc;
+}
+
+}  // extern "C"

@@ -200,3 +200,103 @@ def perturbed_start(views: PlanarViews, seed=1, K=FIXTURE_K, trans=0.02, rot_deg
     intr[2] = K[0, 2] + rng.uniform(-centre_px, centre_px)
     intr[3] = K[1, 2] + rng.uniform(-centre_px, centre_px)
     return intr, q, t
+
+
+# --------------------------------------------------------------------------
+# rig scenes (ExtrinsicsCalibrator): the scenario of reference
+# src/test_extrinsics_calibrator.cpp:40-134, scaled per SURVEY.md App. B (C3)
+# --------------------------------------------------------------------------
+@dataclass
+class RigScene:
+    u: np.ndarray            # normalised image coordinates per observation (float32)
+    v: np.ndarray
+    obs_cam: np.ndarray      # int32
+    obs_point: np.ndarray    # int64 global world_point_id
+    frame_offsets: np.ndarray
+    Xw: np.ndarray           # [n_points,3] float32 (perturbed world points handed to the solver)
+    q_c: np.ndarray          # initial (perturbed) camera_T_rig, [C,4]
+    t_c: np.ndarray
+    cam_frozen: np.ndarray   # uint8
+    q_f: np.ndarray          # initial (perturbed) rig_T_world, [F,4]
+    t_f: np.ndarray
+    q_c_true: np.ndarray
+    t_c_true: np.ndarray
+    q_f_true: np.ndarray
+    t_f_true: np.ndarray
+
+    @property
+    def n_obs(self):
+        return int(self.frame_offsets[-1])
+
+
+def _quat_mul(a, b):
+    w0, x0, y0, z0 = np.moveaxis(a, -1, 0)
+    w1, x1, y1, z1 = np.moveaxis(b, -1, 0)
+    return np.stack([w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1, w0 * x1 + x0 * w1 + y0 * z1 - z0 * y1,
+                     w0 * y1 - x0 * z1 + y0 * w1 + z0 * x1, w0 * z1 + x0 * y1 - y0 * x1 + z0 * w1], axis=-1)
+
+
+def _perturb_pose(rng, q, t, trans, rot_deg):
+    n = q.shape[0]
+    ang = np.deg2rad(rng.uniform(-rot_deg, rot_deg, size=(n, 3))) / 2.0
+    dq = np.concatenate([np.ones((n, 1)), ang], axis=1)
+    dq /= np.linalg.norm(dq, axis=1, keepdims=True)
+    return _quat_mul(q, dq), t + rng.uniform(-trans, trans, size=(n, 3))
+
+
+def rig_scene(n_cams=4, n_frames=1000, grid=(17, 11), pitch=0.02, seed=0, noise_2d=2.0 / 500.0,
+              noise_3d=0.001, cam_trans=0.005, cam_rot_deg=0.1, frame_trans=0.02, frame_rot_deg=1.0,
+              outlier_fraction=0.0, order="frame-major") -> RigScene:
+    """Camera 0 is the identity and frozen; the others sit at U(+-0.03) in x,y.  Each frame looks
+    at a planar lattice of world points from U(0.3,1)^3; every camera sees every point."""
+    rng = np.random.default_rng(seed)
+    C, F = n_cams, n_frames
+    q_c_true = np.tile(np.array([1.0, 0, 0, 0]), (C, 1))
+    t_c_true = np.zeros((C, 3))
+    t_c_true[1:, :2] = rng.uniform(-0.03, 0.03, size=(C - 1, 2))
+    q_c, t_c = _perturb_pose(rng, q_c_true, t_c_true, cam_trans, cam_rot_deg)
+    q_c[0], t_c[0] = q_c_true[0], t_c_true[0]
+    # frames: translation U(0.3,1)^3, rotation rows (forward, right, up) as in the reference test
+    t_f_true = rng.uniform(0.3, 1.0, size=(F, 3))
+    fwd = t_f_true / np.linalg.norm(t_f_true, axis=1, keepdims=True)
+    right = np.cross(np.array([0.0, 1.0, 0.0]), fwd)
+    right /= np.linalg.norm(right, axis=1, keepdims=True)
+    up = np.cross(fwd, right)
+    Rf = np.stack([fwd, right, up], axis=1)
+    q_f_true = rot_to_quat(Rf)
+    q_f, t_f = _perturb_pose(rng, q_f_true, t_f_true, frame_trans, frame_rot_deg)
+    gx, gy = grid
+    xs = (np.arange(gx) - (gx - 1) / 2.0) * pitch
+    ys = (np.arange(gy) - (gy - 1) / 2.0) * pitch
+    # lattice in the plane facing the rig: world axes chosen so that it is seen at depth ~|t|
+    lat = np.stack(np.meshgrid(xs, ys, indexing="ij"), axis=-1).reshape(-1, 2)
+    P = lat.shape[0]
+    pts = np.zeros((F, P, 3))
+    pts[:, :, 1] = lat[:, 0]
+    pts[:, :, 2] = lat[:, 1]
+    # world -> rig -> camera (all cameras)
+    Rc = quat_to_rot(q_c_true)
+    p_rig = np.einsum("fij,fpj->fpi", quat_to_rot(q_f_true), pts) + t_f_true[:, None, :]
+    p_cam = np.einsum("cij,fpj->fcpi", Rc, p_rig) + t_c_true[None, :, None, :]
+    uu = p_cam[..., 0] / p_cam[..., 2] + rng.uniform(-noise_2d, noise_2d, size=p_cam.shape[:-1])
+    vv = p_cam[..., 1] / p_cam[..., 2] + rng.uniform(-noise_2d, noise_2d, size=p_cam.shape[:-1])
+    if outlier_fraction > 0:
+        bad = rng.uniform(size=uu.shape) < outlier_fraction
+        uu = np.where(bad, uu + rng.uniform(-0.05, 0.05, size=uu.shape), uu)
+        vv = np.where(bad, vv + rng.uniform(-0.05, 0.05, size=vv.shape), vv)
+    Xw = (pts + rng.uniform(-noise_3d, noise_3d, size=pts.shape)).reshape(-1, 3).astype(np.float32)
+    pid = np.arange(F * P, dtype=np.int64).reshape(F, P)
+    if order == "frame-major":  # the reference test: per point, every camera (point-major inside a frame)
+        obs_cam = np.tile(np.arange(C, dtype=np.int32), (F, P, 1)).reshape(-1)
+        obs_point = np.repeat(pid[:, :, None], C, axis=2).reshape(-1)
+        u = np.transpose(uu, (0, 2, 1)).reshape(-1)
+        v = np.transpose(vv, (0, 2, 1)).reshape(-1)
+    else:  # camera-major inside a frame
+        obs_cam = np.tile(np.repeat(np.arange(C, dtype=np.int32), P), F)
+        obs_point = np.repeat(pid[:, None, :], C, axis=1).reshape(-1)
+        u, v = uu.reshape(-1), vv.reshape(-1)
+    frame_offsets = np.arange(F + 1, dtype=np.int64) * (C * P)
+    frozen = np.zeros(C, np.uint8)
+    frozen[0] = 1
+    return RigScene(u.astype(np.float32), v.astype(np.float32), obs_cam, obs_point, frame_offsets, Xw,
+                    q_c, t_c, frozen, q_f, t_f, q_c_true, t_c_true, q_f_true, t_f_true)

@@ -1,0 +1,88 @@
+"""GPU parity tests of the rig path (ExtrinsicsCalibrator::Optimize): libccg.so through the
+C-ABI vs the CPU oracle on identical inputs (BASELINE.json tolerances)."""
+import numpy as np
+import pytest
+
+import oracle
+from camera_calibrator_b200 import rig_api, synth
+from helpers import TOL_PARAM, TOL_RMS, block_err, quat_to_rot, rel_err
+
+pytestmark = pytest.mark.gpu
+HUBER = float(np.float32(3.0) / np.float32(500.0))
+
+
+def _args(s):
+    return (s.u, s.v, s.obs_cam, s.obs_point, s.frame_offsets, s.Xw)
+
+
+def test_rig_eval_blocks_match_oracle(ctx):
+    """Residuals (Huber-corrected), V_f, W_f, g_f, block-diagonal U, g_c, robust cost of one sweep."""
+    s = synth.rig_scene(n_cams=3, n_frames=37, grid=(7, 5), seed=3, outlier_fraction=0.1)
+    g = rig_api.rig_eval(ctx, *_args(s), s.q_c, s.t_c, s.q_f, s.t_f, HUBER)
+    r = oracle.rig_eval(*_args(s), s.q_c, s.t_c, s.q_f, s.t_f, HUBER)
+    assert np.max(np.abs(g["res"] - r["res"])) <= 1e-12
+    assert abs(g["cost"] - r["cost"]) <= 1e-12 * r["cost"]
+    assert block_err(g["U"], r["U"]) <= 1e-11
+    assert block_err(g["gu"], r["gu"]) <= 1e-10
+    for f in range(37):
+        for key in ("V", "W", "gv"):
+            assert block_err(g[key][f], r[key][f]) <= 1e-10, (key, f)
+
+
+def _check(got, ref, s):
+    gqc, gtc, gqf, gtf, gcost, grep = got
+    rqc, rtc, rqf, rtf, rcost, rrep = ref
+    assert grep["termination"] in (1, 2, 3)
+    assert np.max(np.abs(quat_to_rot(gqc) - quat_to_rot(rqc))) <= TOL_PARAM
+    assert np.max(np.abs(quat_to_rot(gqf) - quat_to_rot(rqf))) <= TOL_PARAM
+    assert rel_err(gtc[1:], rtc[1:], floor=1e-3) <= TOL_PARAM
+    assert rel_err(gtf, rtf, floor=1e-3) <= TOL_PARAM
+    assert abs(grep["rms"] - rrep["rms"]) <= TOL_RMS
+    # frozen camera untouched, bit-exact
+    assert np.array_equal(gqc[0], s.q_c[0]) and np.array_equal(gtc[0], s.t_c[0])
+    # per-observation final cost, in the caller's observation order
+    assert gcost.shape == rcost.shape
+    assert np.max(np.abs(gcost - rcost)) <= 1e-9 * max(np.max(rcost), 1e-30)
+    assert abs(gcost.sum() - grep["final_cost"]) <= 1e-10 * grep["final_cost"]
+
+
+def test_rig_solve_two_cameras_reference_scenario(ctx):
+    """The reference test's shape (test_extrinsics_calibrator.cpp:40-134): 2 cameras, camera 0
+    frozen, 4 points per frame, all noise sources; fresh object (gauge fixed)."""
+    s = synth.rig_scene(n_cams=2, n_frames=200, grid=(2, 2), pitch=0.2, seed=0)
+    got = rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    ref = oracle.rig_solve(*_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    _check(got, ref, s)
+
+
+def test_rig_solve_four_cameras_with_outliers(ctx):
+    """C3 shape reduced: 4 cameras x 120 frames x 35 points, 5 % gross outliers (Huber active)."""
+    s = synth.rig_scene(n_cams=4, n_frames=120, grid=(7, 5), seed=2, outlier_fraction=0.05)
+    got = rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    ref = oracle.rig_solve(*_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    _check(got, ref, s)
+    assert np.count_nonzero(ref[4] > 0.5 * HUBER * HUBER) > 0  # some observations are in the linear zone
+
+
+def test_rig_observation_order_is_preserved(ctx):
+    """Camera-major and point-major insertion orders give the same solution and the cost of every
+    observation lands at its own index (ids bit-exact)."""
+    a = synth.rig_scene(n_cams=3, n_frames=30, grid=(4, 3), seed=5, order="frame-major")
+    b = synth.rig_scene(n_cams=3, n_frames=30, grid=(4, 3), seed=5, order="camera-major")
+    ga = rig_api.rig_solve(ctx, *_args(a), a.q_c, a.t_c, a.cam_frozen, a.q_f, a.t_f)
+    gb = rig_api.rig_solve(ctx, *_args(b), b.q_c, b.t_c, b.cam_frozen, b.q_f, b.t_f)
+    assert np.max(np.abs(ga[1] - gb[1])) <= 1e-9
+    key_a = {(int(f), int(c), int(p)): i for i, (f, c, p) in enumerate(
+        zip(np.repeat(np.arange(30), 36), a.obs_cam, a.obs_point))}
+    for j, (f, c, p) in enumerate(zip(np.repeat(np.arange(30), 36), b.obs_cam, b.obs_point)):
+        i = key_a[(int(f), int(c), int(p))]
+        assert abs(ga[4][i] - gb[4][j]) <= 1e-9 * max(ga[4][i], 1e-12)
+
+
+def test_rig_too_many_cameras_is_reported(ctx):
+    import camera_calibrator_b200 as cc
+
+    s = synth.rig_scene(n_cams=6, n_frames=4, grid=(2, 2), seed=1)
+    with pytest.raises(cc.CcgError) as e:
+        rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    assert e.value.status == -5
