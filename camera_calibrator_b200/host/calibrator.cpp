@@ -1,0 +1,218 @@
+// Host side of calibrator::Calibrator (reference src/calibrator.cpp): float->double
+// packing exactly where the reference does it (calibrator.cpp:245-303), the solve
+// itself behind ccg_intrinsics_solve, float write-back of K and distortion only
+// (calibrator.cpp:326-335).
+#include "calibrator.hh"
+
+#include <cmath>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/ccg.h"
+#include "geometry.hh"
+
+namespace calibrator {
+
+namespace {
+struct CtxHolder {
+  ccg_ctx* ctx = nullptr;
+  ~CtxHolder() {
+    if (ctx) ccg_destroy(ctx);
+  }
+};
+}  // namespace
+
+ccg_ctx* HostContext() {
+  thread_local CtxHolder holder;
+  if (!holder.ctx) {
+    int device = 0;
+    if (const char* e = std::getenv("CCG_DEVICE")) device = std::atoi(e);
+    const int rc = ccg_init(device, &holder.ctx);
+    if (rc != CCG_OK)
+      throw std::runtime_error(std::string("camera_calibrator_b200: no usable CUDA device (") +
+                               ccg_status_string(rc) + "); there is no CPU fallback");
+  }
+  return holder.ctx;
+}
+
+// intrinsic block order, reference calibrator.cpp:168-179
+enum { OFF_FX = 0, OFF_FY, OFF_PX, OFF_PY, OFF_K1, OFF_K2, OFF_P1, OFF_P2, OFF_K3, NUM_INTR };
+
+Calibrator::Calibrator(const int img_width, const int img_height) : width_(img_width), height_(img_height) {}
+
+void Calibrator::EstimateOpenCv(const std::vector<Points2D>&, const std::vector<Points3D>&) {
+  throw std::runtime_error(
+      "Calibrator::EstimateOpenCv delegates to cv::calibrateCamera in the reference; OpenCV C++ is not part "
+      "of this build (out of scope). Use Estimate().");
+}
+
+void Calibrator::Estimate(const std::vector<Points2D>& in_img_points,
+                          const std::vector<Points3D>& in_world_points) {
+  if (in_img_points.size() != in_world_points.size())
+    throw std::invalid_argument("Calibrator::Estimate: image/world view counts differ");
+  std::vector<Matrix3> Hs;
+  Hs.reserve(in_img_points.size());
+  for (size_t i = 0; i < in_img_points.size(); ++i)
+    Hs.push_back(EstimateHomography(in_world_points[i], in_img_points[i]));
+  K_ = EstimateKFromHomographies(Hs);
+  std::vector<Quaternion> qs;
+  std::vector<Point3D> ts;
+  const Matrix3 K_inv = K_.inverse();
+  for (const auto& H : Hs) {
+    const auto [R, t] = RecoverExtrinsics(K_inv, H);
+    qs.emplace_back(R);
+    ts.push_back(t);
+  }
+  Optimize(in_img_points, in_world_points, qs, ts);
+}
+
+void Calibrator::Optimize(const std::vector<Points2D>& in_img_points,
+                          const std::vector<Points3D>& in_world_points, std::vector<Quaternion>& qs,
+                          std::vector<Point3D>& ts) {
+  const size_t n_img = in_img_points.size();
+  if (n_img != in_world_points.size() || n_img != qs.size() || n_img != ts.size())
+    throw std::invalid_argument("Calibrator::Optimize: per-view argument sizes differ");
+  std::vector<int64_t> off(n_img + 1, 0);
+  for (size_t i = 0; i < n_img; ++i) {
+    if (in_img_points[i].size() != in_world_points[i].size())
+      throw std::invalid_argument("Calibrator::Optimize: point counts differ in a view");
+    off[i + 1] = off[i] + (int64_t)in_img_points[i].size();
+  }
+  const size_t n = (size_t)off[n_img];
+  std::vector<float> u(n), v(n), X(n), Y(n), Z(n);
+  std::vector<double> q(4 * n_img), t(3 * n_img);
+  for (size_t i = 0; i < n_img; ++i) {
+    q[4 * i + 0] = qs[i].w();
+    q[4 * i + 1] = qs[i].x();
+    q[4 * i + 2] = qs[i].y();
+    q[4 * i + 3] = qs[i].z();
+    t[3 * i + 0] = ts[i].x();
+    t[3 * i + 1] = ts[i].y();
+    t[3 * i + 2] = ts[i].z();
+    size_t o = (size_t)off[i];
+    for (size_t j = 0; j < in_img_points[i].size(); ++j, ++o) {
+      u[o] = in_img_points[i][j].x();
+      v[o] = in_img_points[i][j].y();
+      X[o] = in_world_points[i][j].x();
+      Y[o] = in_world_points[i][j].y();
+      Z[o] = in_world_points[i][j].z();
+    }
+  }
+  double intr[NUM_INTR];
+  intr[OFF_FX] = K_(0, 0);
+  intr[OFF_FY] = K_(1, 1);
+  intr[OFF_PX] = K_(0, 2);
+  intr[OFF_PY] = K_(1, 2);
+  intr[OFF_K1] = dist_(0);
+  intr[OFF_K2] = dist_(1);
+  intr[OFF_P1] = dist_(2);
+  intr[OFF_P2] = dist_(3);
+  intr[OFF_K3] = dist_(4);
+  uint32_t mask = 0;
+  for (int idx : constant_intrinsics_)
+    if (idx >= 0 && idx < NUM_INTR) mask |= 1u << idx;
+
+  ccg_opts opts;
+  ccg_default_opts(&opts);
+  opts.max_iterations = 100;  // calibrator.cpp:319
+  ccg_report rep;
+  ccg_ctx* ctx = HostContext();
+  const int rc = ccg_intrinsics_solve(ctx, u.data(), v.data(), X.data(), Y.data(), Z.data(), off.data(),
+                                      (int64_t)n_img, intr, q.data(), t.data(), mask, &opts, &rep);
+  if (rc != CCG_OK)
+    throw std::runtime_error(std::string("Calibrator::Optimize: ") + ccg_status_string(rc) + " " +
+                             ccg_last_error(ctx));
+  report_.iterations = rep.iterations;
+  report_.accepted = rep.accepted;
+  report_.rejected = rep.rejected;
+  report_.sweeps = rep.sweeps;
+  report_.termination = rep.termination;
+  report_.initial_cost = rep.initial_cost;
+  report_.final_cost = rep.final_cost;
+  report_.gradient_norm = rep.gradient_norm;
+  report_.rms = rep.rms;
+  opt_q_.resize(n_img);
+  opt_t_.resize(n_img);
+  for (size_t i = 0; i < n_img; ++i) {
+    opt_q_[i] = {q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]};
+    opt_t_[i] = {t[3 * i], t[3 * i + 1], t[3 * i + 2]};
+  }
+  // Put params back (float32, K and distortion only)
+  K_(0, 0) = static_cast<float>(intr[OFF_FX]);
+  K_(1, 1) = static_cast<float>(intr[OFF_FY]);
+  K_(0, 2) = static_cast<float>(intr[OFF_PX]);
+  K_(1, 2) = static_cast<float>(intr[OFF_PY]);
+  dist_(0) = static_cast<float>(intr[OFF_K1]);
+  dist_(1) = static_cast<float>(intr[OFF_K2]);
+  dist_(2) = static_cast<float>(intr[OFF_P1]);
+  dist_(3) = static_cast<float>(intr[OFF_P2]);
+  dist_(4) = static_cast<float>(intr[OFF_K3]);
+}
+
+void Calibrator::GetOptimizedPoses(std::vector<std::array<double, 4>>* qs,
+                                   std::vector<std::array<double, 3>>* ts) const {
+  if (qs) *qs = opt_q_;
+  if (ts) *ts = opt_t_;
+}
+
+void Calibrator::ForceDistortionToConstant(const int distortion_idx) {
+  constant_intrinsics_.insert(distortion_idx + static_cast<int>(OFF_K1));
+}
+
+namespace {
+template <typename T>
+inline void lens(T k1, T k2, T k3, T p1, T p2, T x, T y, T* xd, T* yd) {
+  const T r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+  const T m = T(1) + k1 * r2 + k2 * r4 + k3 * r6;
+  *xd = x * m + T(2) * p1 * x * y + p2 * (r2 + T(2) * x * x);
+  *yd = y * m + T(2) * p2 * x * y + p1 * (r2 + T(2) * y * y);
+}
+}  // namespace
+
+Points2D Calibrator::Undistort(const Points2D& img_points) {
+  // The reference solves, per point, a 2-unknown least-squares problem with Ceres
+  // (DENSE_QR, <= 1000 iterations) starting from the distorted coordinates.  Here the
+  // same fixed point is found with damped Newton steps on the 2x2 system in double.
+  const Matrix3 K_inv = K_.inverse();
+  const double k1 = dist_(0), k2 = dist_(1), p1 = dist_(2), p2 = dist_(3), k3 = dist_(4);
+  Points2D out;
+  out.reserve(img_points.size());
+  for (const auto& p : img_points) {
+    const float w = K_inv(2, 0) * p.x() + K_inv(2, 1) * p.y() + K_inv(2, 2);
+    const double xt = (K_inv(0, 0) * p.x() + K_inv(0, 1) * p.y() + K_inv(0, 2)) / w;
+    const double yt = (K_inv(1, 0) * p.x() + K_inv(1, 1) * p.y() + K_inv(1, 2)) / w;
+    double x = xt, y = yt;
+    for (int it = 0; it < 1000; ++it) {
+      double xd, yd;
+      lens(k1, k2, k3, p1, p2, x, y, &xd, &yd);
+      const double ex = xd - xt, ey = yd - yt;
+      const double r2 = x * x + y * y, r4 = r2 * r2;
+      const double m = 1.0 + k1 * r2 + k2 * r4 + k3 * r4 * r2, mp = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
+      const double a = m + 2.0 * x * x * mp + 2.0 * p1 * y + 6.0 * p2 * x;
+      const double b = 2.0 * x * y * mp + 2.0 * p1 * x + 2.0 * p2 * y;
+      const double d = m + 2.0 * y * y * mp + 2.0 * p2 * x + 6.0 * p1 * y;
+      const double det = a * d - b * b;
+      if (!(std::fabs(det) > 1e-300)) break;
+      const double dx = (d * ex - b * ey) / det, dy = (a * ey - b * ex) / det;
+      x -= dx;
+      y -= dy;
+      if (std::fabs(dx) + std::fabs(dy) <= 1e-16 * (1.0 + std::fabs(x) + std::fabs(y))) break;
+    }
+    out.emplace_back((float)x, (float)y);
+  }
+  return out;
+}
+
+Points2D Calibrator::Distort(const Points2D& normalized_points) {
+  Points2D out;
+  out.reserve(normalized_points.size());
+  for (const auto& p : normalized_points) {
+    float xd, yd;  // float arithmetic, as the reference instantiates DistortPixels here
+    lens<float>(dist_(0), dist_(1), dist_(4), dist_(2), dist_(3), p.x(), p.y(), &xd, &yd);
+    out.emplace_back(K_(0, 0) * xd + K_(0, 2), K_(1, 1) * yd + K_(1, 2));
+  }
+  return out;
+}
+
+}  // namespace calibrator

@@ -1,0 +1,70 @@
+"""Launched with torchrun --nproc-per-node N: a view-partitioned single-camera solve and a
+frame-partitioned rig solve over NCCL must reproduce the single-GPU results."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import camera_calibrator_b200 as cc
+from camera_calibrator_b200 import partition, rig_api, synth
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctx = cc.Context(local)
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    uid.copy_(torch.tensor(list(cc.Context.comm_unique_id()), dtype=torch.uint8))
+dist.broadcast(uid, 0)
+ctx.comm_init(rank, world, bytes(uid.cpu().tolist()))
+
+# ---- single camera, views partitioned
+V, P = 3000, 120
+full = synth.planar_views(V, P, seed=5)
+intr, q, t = synth.perturbed_start(full)
+a, b = partition.split_range(V, world, rank)
+(u, v, X, Y, Z), off = partition.slice_views([full.u, full.v, full.X, full.Y, full.Z], full.view_offsets, a, b)
+p = ctx.intrinsics_problem(u, v, X, Y, Z, off, intr, q[a:b], t[a:b], shared=True)
+tm = p.run(cc.default_opts(profile=1))
+gi, gq, gt, rep = p.download()
+ok = True
+if rank == 0:
+    ctx1 = cc.Context(local)
+    ri, rq, rt, rrep = ctx1.intrinsics_solve(full.u, full.v, full.X, full.Y, full.Z, full.view_offsets, intr, q, t)
+    e_i = float(np.max(np.abs(gi[0] - ri) / np.abs(ri)))
+    e_r = abs(rep[0]["rms"] - rrep["rms"])
+    e_t = float(np.max(np.abs(gt - rt[a:b])))
+    print(f"[intr] world {world}: intr rel err {e_i:.2e}  |d rms| {e_r:.2e}  pose t err {e_t:.2e}  "
+          f"iters {rep[0]['iterations']} vs {rrep['iterations']}  allreduces {tm['allreduces']}  total {tm['total_ms']:.2f} ms")
+    ok &= e_i <= 1e-6 and e_r <= 1e-9
+all_i = [torch.zeros(9, dtype=torch.float64, device="cuda") for _ in range(world)]
+dist.all_gather(all_i, torch.tensor(gi[0], device="cuda"))
+ok &= all(torch.equal(all_i[0], x) for x in all_i)  # replicated state is bit-identical on every rank
+
+# ---- rig, frames partitioned
+s = synth.rig_scene(n_cams=4, n_frames=400, grid=(7, 5), seed=6)
+fa, fb = partition.split_range(400, world, rank)
+o0, o1 = int(s.frame_offsets[fa]), int(s.frame_offsets[fb])
+rp = rig_api.RigProblem(ctx, s.u[o0:o1], s.v[o0:o1], s.obs_cam[o0:o1], s.obs_point[o0:o1],
+                        s.frame_offsets[fa:fb + 1] - o0, s.Xw, s.q_c, s.t_c, s.cam_frozen, s.q_f[fa:fb],
+                        s.t_f[fa:fb], shared=True)
+rtm = rp.run()
+gqc, gtc, gqf, gtf, gcost, grep = rp.download()
+if rank == 0:
+    rqc, rtc, rqf, rtf, rcost, rrep = rig_api.rig_solve(ctx1, s.u, s.v, s.obs_cam, s.obs_point, s.frame_offsets, s.Xw,
+                                                        s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    e_c = float(np.max(np.abs(gtc - rtc)))
+    e_r = abs(grep["rms"] - rrep["rms"])
+    print(f"[rig ] world {world}: t_c err {e_c:.2e}  |d rms| {e_r:.2e}  iters {grep['iterations']} vs "
+          f"{rrep['iterations']}  allreduces {rtm['allreduces']}")
+    ok &= e_c <= 1e-6 and e_r <= 1e-9
+flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTI_GPU_CHECK", "PASS" if flag.item() == 1.0 else "FAIL")
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1.0 else 1)
