@@ -41,6 +41,8 @@ class Opts(C.Structure):
         ("parameter_tolerance", C.c_double),
         ("huber_a", C.c_double),
         ("noise_factor", C.c_double),
+        ("hessian_fp64", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

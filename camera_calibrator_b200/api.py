@@ -112,7 +112,7 @@ class Context:
         self._check(rc, "ccg_intrinsics_solve_batch")
         return intr, q, t, [r.asdict() for r in reps]
 
-    def intrinsics_eval(self, u, v, X, Y, Z, view_offsets, intr, q, t):
+    def intrinsics_eval(self, u, v, X, Y, Z, view_offsets, intr, q, t, hessian_fp64=False):
         u, v, X, Y, Z = map(f32, (u, v, X, Y, Z))
         off = i64(view_offsets)
         nv = len(off) - 1
@@ -132,7 +132,7 @@ class Context:
             ptr(Z, C.c_float), ptr(off, C.c_int64), C.c_int64(nv), ptr(intr, C.c_double),
             ptr(q, C.c_double), ptr(t, C.c_double), ptr(res, C.c_double), ptr(Vb, C.c_double),
             ptr(Wb, C.c_double), ptr(gv, C.c_double), ptr(U, C.c_double), ptr(gu, C.c_double),
-            ptr(cost, C.c_double))
+            ptr(cost, C.c_double), C.c_int(1 if hessian_fp64 else 0))
         self._check(rc, "ccg_intrinsics_eval")
         return dict(res=res.reshape(n, 2), V=Vb, W=Wb, gv=gv, U=U, gu=gu, cost=float(cost[0]))
 

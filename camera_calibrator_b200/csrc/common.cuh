@@ -60,6 +60,7 @@ struct LmParams {
   double function_tolerance, gradient_tolerance, parameter_tolerance;
   double huber_a;
   double noise_factor;
+  int hessian_fp64;
 };
 
 inline LmParams to_params(const ccg_opts& o) {
@@ -76,6 +77,7 @@ inline LmParams to_params(const ccg_opts& o) {
   p.parameter_tolerance = o.parameter_tolerance;
   p.huber_a = o.huber_a;
   p.noise_factor = o.noise_factor;
+  p.hessian_fp64 = o.hessian_fp64;
   return p;
 }
 

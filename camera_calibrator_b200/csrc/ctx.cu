@@ -149,6 +149,8 @@ void ccg_default_opts(ccg_opts* o) {
   o->gradient_tolerance = 1e-12;
   o->parameter_tolerance = 1e-9;
   o->noise_factor = 4.0;
+  o->hessian_fp64 = 0;
+  o->reserved_ = 0;
   o->huber_a = (double)(3.0f / 500.0f);
 }
 

@@ -335,6 +335,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep(IntrDev d, double
   }
 }
 
+}  // namespace ccg
+#include "intr_mixed.cuh"
+namespace ccg {
+
 // --------------------------------------------------------------------------
 // pose elimination, one THREAD per view: Cholesky of V + lambda D, T = L^-1 [W g_v],
 // Y = L^-T T (stored for the back-substitution), contributions T'T and T't_g to the
@@ -689,6 +693,7 @@ struct ccg_intr_problem {
   double *d_intr0 = nullptr, *d_pose0 = nullptr, *d_meas_scale = nullptr;
   int2* d_item_ranges = nullptr;
   float* d_obs = nullptr;
+  int group = 32;                    // lanes per view in the mixed-precision sweep (8, 16 or 32)
   std::vector<int64_t> problem_off;  // host copy
   std::vector<int64_t> problem_obs;  // observations per problem
   LmParams params;
@@ -730,6 +735,9 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   p->n_obs = n_obs;
   cudaStream_t st = ctx->stream;
 
+  // lanes per view in the mixed sweep: small views share a warp (8 or 16 lanes each)
+  const double mean_obs = n_views > 0 ? (double)n_obs / (double)n_views : 0.0;
+  p->group = mean_obs <= 96.0 ? 8 : (mean_obs <= 224.0 ? 16 : 32);
   // ---- work items: consecutive views of one problem per CTA
   const int64_t target_items = (int64_t)ctx->sm_count * 4;
   int64_t vpi = std::max<int64_t>(kWarps / 2, (n_views + target_items - 1) / std::max<int64_t>(target_items, 1));
@@ -838,6 +846,21 @@ int reset_problem(ccg_intr_problem* p, const LmParams& P) {
 
 enum { TAG_SWEEP = 0, TAG_SCHUR = 1, TAG_SMALL = 2 };
 
+// the sweep kernel variant: FP64 warp pairs, or mixed precision with G lanes per view
+void launch_sweep(ccg_intr_problem* p, const LmParams& P, double* res_out) {
+  cudaStream_t st = p->ctx->stream;
+  if (P.hessian_fp64) {
+    k_intr_sweep<<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
+  } else if (p->group == 8) {
+    k_intr_sweep_mixed<8><<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
+  } else if (p->group == 16) {
+    k_intr_sweep_mixed<16><<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
+  } else {
+    k_intr_sweep_mixed<32><<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
+  }
+  p->ctx->launches++;
+}
+
 // one residual+Jacobian sweep followed by the accept/reject step
 int launch_sweep_decide(ccg_intr_problem* p, const LmParams& P, Profiler& prof, double* res_out, int* n_allreduce) {
   ccg_ctx* ctx = p->ctx;
@@ -845,9 +868,8 @@ int launch_sweep_decide(ccg_intr_problem* p, const LmParams& P, Profiler& prof, 
   cudaStream_t st = ctx->stream;
   const int nb = (int)p->n_problems;
   prof.begin(TAG_SWEEP);
-  k_intr_sweep<<<p->n_items, kWarps * 32, 0, st>>>(d, res_out);
+  launch_sweep(p, P, res_out);
   prof.end();
-  ctx->launches++;
   prof.begin(TAG_SMALL);
   if (p->shared && ctx->world > 1) {
     k_intr_reduce_sweep<<<nb, kRedSeg * kSweepPart, 0, st>>>(d);
@@ -1070,11 +1092,10 @@ int ccg_intrinsics_time_sweep(ccg_intr_problem* p, int n, float* ms_per_launch) 
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  k_intr_sweep<<<p->n_items, kWarps * 32, 0, ctx->stream>>>(p->dev, nullptr);  // warm-up
+  launch_sweep(p, P, nullptr);  // warm-up
   cudaEventRecord(e0, ctx->stream);
-  for (int i = 0; i < n; ++i) k_intr_sweep<<<p->n_items, kWarps * 32, 0, ctx->stream>>>(p->dev, nullptr);
+  for (int i = 0; i < n; ++i) launch_sweep(p, P, nullptr);
   cudaEventRecord(e1, ctx->stream);
-  ctx->launches += n + 1;
   CCG_CUDA(ctx, cudaEventSynchronize(e1));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
@@ -1139,7 +1160,7 @@ int ccg_intrinsics_eval(ccg_ctx* ctx, const float* u, const float* v, const floa
                         const float* Y, const float* Z, const int64_t* view_offsets,
                         int64_t n_views, const double* intr, const double* q, const double* t,
                         double* res, double* Vb, double* Wb, double* gvb, double* U, double* gu,
-                        double* cost) {
+                        double* cost, int hessian_fp64) {
   ccg_intr_problem* p = nullptr;
   const int64_t poff[2] = {0, n_views};
   int rc = ccg_intrinsics_create(ctx, u, v, X, Y, Z, view_offsets, n_views, poff, 1, intr, q, t, 0, 0, &p);
@@ -1147,6 +1168,7 @@ int ccg_intrinsics_eval(ccg_ctx* ctx, const float* u, const float* v, const floa
   auto body = [&]() -> int {
     ccg_opts o;
     ccg_default_opts(&o);
+    o.hessian_fp64 = hessian_fp64;
     const LmParams P = to_params(o);
     CCG_TRY(reset_problem(p, P));
     double* d_res = nullptr;

@@ -52,6 +52,9 @@ typedef struct {
   double huber_a;               /* rig only: (double)(3.0f/500.0f), extrinsics_calibrator.cpp:176; <= 0: no loss */
   double noise_factor;          /* 4: a step whose predicted decrease is <= noise_factor * (eps/2) * max|measurement| *
                                    sqrt(2 cost) is below the FP64 resolution of the cost: take it and stop */
+  int32_t hessian_fp64;         /* 0 (default): single-camera sweep forms J'J in FP32 (residual, cost and gradient stay
+                                   FP64; same fixed point); 1: everything in FP64 */
+  int32_t reserved_;
 } ccg_opts;
 
 typedef struct {
@@ -127,12 +130,13 @@ int ccg_intrinsics_solve_batch(ccg_ctx* ctx, const float* u, const float* v, con
  * (the blocks the LM loop consumes), for parity tests.  Any output may be NULL.
  *   res 2/obs | Vb 36/view (6x6) | Wb 54/view (6x9) | gvb 6/view | U 81 | gu 9 | cost 1
  * Tangent order per view: rotation (half-angle vector, Ceres QuaternionManifold
- * convention) then translation. */
+ * convention) then translation.  hessian_fp64 selects the sweep variant (see ccg_opts): with 0
+ * V, W, U carry FP32 rounding (~1e-6 relative), res, gvb, gu, cost are FP64 in both. */
 int ccg_intrinsics_eval(ccg_ctx* ctx, const float* u, const float* v, const float* X,
                         const float* Y, const float* Z, const int64_t* view_offsets,
                         int64_t n_views, const double* intr, const double* q, const double* t,
                         double* res, double* Vb, double* Wb, double* gvb, double* U, double* gu,
-                        double* cost);
+                        double* cost, int hessian_fp64);
 
 /* Device-resident form of the same solve: upload once, run many times.
  * shared != 0 (requires ccg_comm_init): the views given here are this rank's
