@@ -40,7 +40,10 @@ WORKLOADS = {
     "c4": (50, 54, 4096),
     "c5": (100000, 400, 1),
 }
-FLOP_PER_OBS = 716.0  # FP64 flops per observation per sweep of the current kernel pair
+# per observation per sweep of the default (mixed-precision) sweep kernel, counted in its SASS loop
+# body: 56 DFMA + 28 DMUL + 19 DADD and 192 FFMA + 48 FMUL + 38 FADD
+FP64_FLOP_PER_OBS = 159.0
+FP32_FLOP_PER_OBS = 470.0
 
 
 def algorithmic_bytes(n_obs, n_views):
@@ -329,7 +332,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        traffic = tj.get(args.workload, {}).get("k_intr_sweep_dram_bytes_per_launch")
+        traffic = tj.get(args.workload, {}).get("sweep_dram_bytes_per_launch")
 
     # ---- end to end through the C-ABI with host buffers (H2D + solve + D2H timed)
     hu, hv, hX, hY, hZ = (pinned(a) for a in (d.u, d.v, d.X, d.Y, d.Z))
@@ -377,13 +380,15 @@ def run_ours(args):
             "breakdown_ms_per_step": {"sweep": sweep_ms / args.steps, "eliminate": schur_ms / args.steps,
                                       "reduce+decide+solve(+allreduce)": small_ms / args.steps,
                                       "allreduces_per_step": n_allreduce / args.steps},
-            "roofline": {"kernel": "k_intr_sweep", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"kernel": "k_intr_sweep_mixed", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src, "launch_ms": sweep_ms_avg, "launches": n_sweeps,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "fp64": {"achieved_tflops": FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
-                                  "peak_tflops": fp64_peak, "flop_per_obs": FLOP_PER_OBS,
-                                  "peak_source": "DFMA micro-benchmark run in this process"}},
+                         "fp64": {"achieved_tflops": FP64_FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
+                                  "peak_tflops": fp64_peak, "flop_per_obs": FP64_FLOP_PER_OBS,
+                                  "peak_source": "DFMA micro-benchmark run in this process"},
+                         "fp32": {"achieved_tflops": FP32_FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
+                                  "flop_per_obs": FP32_FLOP_PER_OBS}},
             "cpu_baseline": {"value": cpu_v, "unit": "obs/s", "cores": oracle.num_threads(), "kind": "port",
                              "sample": sample[5], "seconds": cpu_dt},
             "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": int(allsum(float(h2d))) if world > 1 else int(h2d),

@@ -132,6 +132,22 @@ __host__ __device__ inline void lm_init(LmState& s, const LmParams& P) {
 // relative cost noise tolerated when a final sub-resolution step is taken
 constexpr double kCostNoise = 1e-12;
 
+// 1/x to within ~1 ulp without the IEEE slow path: hardware seed (~20 bits) + two Newton steps.
+// Used for the perspective division of the sweeps (the same function evaluates the current and
+// the candidate cost, so LM's gain ratio is unaffected).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+__device__ __forceinline__ float fast_rcpf(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ double clampd(double x, double lo, double hi) {
   return fmin(fmax(x, lo), hi);
 }

@@ -66,6 +66,7 @@ struct IntrDev {
   IntrState* ps;
   int* n_done;
   int64_t obs_base;   // view_off[0]
+  int schur_split;    // CTAs of the elimination kernel per work item
 };
 
 // --------------------------------------------------------------------------
@@ -84,7 +85,7 @@ __device__ __forceinline__ void obs_geometry(const double (&R)[9], const double 
   const double y0 = R[0] * X + R[1] * Y + R[2] * Z;
   const double y1 = R[3] * X + R[4] * Y + R[5] * Z;
   const double y2 = R[6] * X + R[7] * Y + R[8] * Z;
-  const double iz = 1.0 / (y2 + t[2]);
+  const double iz = fast_rcp(y2 + t[2]);
   const double xn = (y0 + t[0]) * iz, yn = (y1 + t[1]) * iz;
   const double fx = k[0], fy = k[1], k1 = k[4], k2 = k[5], p1 = k[6], p2 = k[7], k3 = k[8];
   const double r2 = xn * xn + yn * yn, r4 = r2 * r2, r6 = r4 * r2;
@@ -358,7 +359,15 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_intr_schur(IntrDev d, LmPa
   __shared__ double s_part[kSchurWarps][kSchurPart];
   __shared__ int s_meta[2];
   __shared__ double s_lambda;
-  const WorkItem it = d.items[blockIdx.x];
+  // d.schur_split CTAs share one work item (the sweep wants few, long items; this kernel many)
+  WorkItem it = d.items[blockIdx.x / d.schur_split];
+  {
+    const int sub = blockIdx.x % d.schur_split, nv = it.v1 - it.v0;
+    const int a = it.v0 + (int)((int64_t)nv * sub / d.schur_split);
+    const int b = it.v0 + (int)((int64_t)nv * (sub + 1) / d.schur_split);
+    it.v0 = a;
+    it.v1 = b;
+  }
   IntrState& ps = d.ps[it.problem];
   if (threadIdx.x == 0) {
     s_meta[0] = ps.lm.par;
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_reduce_schur(Intr
   __shared__ double s_buf[kRedSeg * kSchurPart];
   IntrState& ps = d.ps[blockIdx.x];
   if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
-  block_reduce_items<kSchurPart>(d.schur_part, ps.item0, ps.item1, s_buf);
+  block_reduce_items<kSchurPart>(d.schur_part, ps.item0 * d.schur_split, ps.item1 * d.schur_split, s_buf);
   if (threadIdx.x < kSchurPart) d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x] = s_buf[threadIdx.x];
 }
 
@@ -589,7 +598,7 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
   IntrState& ps = d.ps[blockIdx.x];
   if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
   if (REDUCE) {
-    block_reduce_items<kSchurPart>(d.schur_part, ps.item0, ps.item1, s_buf);
+    block_reduce_items<kSchurPart>(d.schur_part, ps.item0 * d.schur_split, ps.item1 * d.schur_split, s_buf);
   } else {
     if (threadIdx.x < kSchurPart) s_buf[threadIdx.x] = d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x];
     __syncthreads();
@@ -739,7 +748,9 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   const double mean_obs = n_views > 0 ? (double)n_obs / (double)n_views : 0.0;
   p->group = mean_obs <= 96.0 ? 8 : (mean_obs <= 224.0 ? 16 : 32);
   // ---- work items: consecutive views of one problem per CTA
-  const int64_t target_items = (int64_t)ctx->sm_count * 4;
+  // one CTA per SM for a big problem (255-register kernels: one resident CTA per SM, so more
+  // items only add wave-quantisation tail); small problems get one item each
+  const int64_t target_items = (int64_t)ctx->sm_count;
   int64_t vpi = std::max<int64_t>(kWarps / 2, (n_views + target_items - 1) / std::max<int64_t>(target_items, 1));
   std::vector<WorkItem> items;
   std::vector<int2> ranges((size_t)n_problems);
@@ -782,7 +793,11 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   CCG_TRY(dev_alloc(p, &d.blk[1], (size_t)n_views * kBlk));
   CCG_TRY(dev_alloc(p, &d.yz, (size_t)n_views * kYz));
   CCG_TRY(dev_alloc(p, &d.sweep_part, items.size() * kSweepPart));
-  CCG_TRY(dev_alloc(p, &d.schur_part, items.size() * kSchurPart));
+  // elimination: 64 views per CTA pass; enough CTAs per item to fill the machine ~8x over
+  int64_t max_item_views = 1;
+  for (const WorkItem& w : items) max_item_views = std::max<int64_t>(max_item_views, w.v1 - w.v0);
+  const int schur_split = (int)std::max<int64_t>(1, std::min<int64_t>((max_item_views + 127) / 128, 16));
+  CCG_TRY(dev_alloc(p, &d.schur_part, items.size() * (size_t)schur_split * kSchurPart));
   CCG_TRY(dev_alloc(p, &d.red_sweep, (size_t)n_problems * kSweepPart));
   CCG_TRY(dev_alloc(p, &d.red_schur, (size_t)n_problems * kSchurPart));
   CCG_TRY(dev_alloc(p, &d.ps, (size_t)n_problems));
@@ -799,6 +814,7 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   d.view_off = d_voff;
   d.items = d_items;
   d.obs_base = 0;
+  d.schur_split = schur_split;
   CCG_CUDA(ctx, cudaMemcpyAsync(obs, u + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(obs + n_obs, v + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(obs + 2 * n_obs, X + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
@@ -891,7 +907,7 @@ int launch_schur_solve(ccg_intr_problem* p, const LmParams& P, Profiler& prof, i
   cudaStream_t st = ctx->stream;
   const int nb = (int)p->n_problems;
   prof.begin(TAG_SCHUR);
-  k_intr_schur<<<p->n_items, kSchurWarps * 32, 0, st>>>(d, P);
+  k_intr_schur<<<p->n_items * d.schur_split, kSchurWarps * 32, 0, st>>>(d, P);
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep_mixed(IntrDev d, 
   __shared__ int s_meta[2];
   __shared__ double s_u[kWarps][NG][41];
   __shared__ double s_g[kWarps][NG][12];  // g_u 9 | sum r^2 | g'd | d'Dd
+  __shared__ float s_pose[kWarps][NG][12];  // float copy of the candidate R (9) and t (3) of the view in flight
   const WorkItem it = d.items[blockIdx.x];
   IntrState& ps = d.ps[it.problem];
   if (threadIdx.x == 0) {
@@ -86,7 +87,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep_mixed(IntrDev d, 
     const bool has_view = v < it.v1;
     // ---------------- candidate pose of this group's view: current (+) (-z - Y du)
     double R[9], t[3];
-    float Rf[9], tf[3];
     {
       double dl = 0.0;
       const int64_t vv = has_view ? v : it.v0;
@@ -118,11 +118,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep_mixed(IntrDev d, 
         pn[gl] = val;
       }
       quat_to_rot(qn, R);
+      // the FP32 pass reads its pose from shared memory: keeping a second register copy forces
+      // the compiler to re-convert R every iteration (12 F2F per observation)
+      __syncwarp();
+      for (int e = gl; e < 12; e += G) {  // G may be 8: a lane can own two entries
+        double val = t[0];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) Rf[i] = (float)R[i];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) tf[i] = (float)t[i];
+        for (int i = 0; i < 9; ++i) val = (e == i) ? R[i] : val;
+        val = (e == 10) ? t[1] : (e == 11) ? t[2] : val;
+        s_pose[warp][grp][e] = (float)val;
+      }
+      __syncwarp();
     }
+    const float* Rf = s_pose[warp][grp];
+    const float* tf = Rf + 9;
     float acc[kNH];
 #pragma unroll
     for (int i = 0; i < kNH; ++i) acc[i] = 0.0f;
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep_mixed(IntrDev d, 
         const double y0 = R[0] * X + R[1] * Y + R[2] * Z;
         const double y1 = R[3] * X + R[4] * Y + R[5] * Z;
         const double y2 = R[6] * X + R[7] * Y + R[8] * Z;
-        const double iz = 1.0 / (y2 + t[2]);
+        const double iz = fast_rcp(y2 + t[2]);
         const double xn = (y0 + t[0]) * iz, yn = (y1 + t[1]) * iz;
         const double r2 = xn * xn + yn * yn, r4 = r2 * r2, r6 = r4 * r2;
         const double m = 1.0 + k[4] * r2 + k[5] * r4 + k[8] * r6;
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep_mixed(IntrDev d, 
         const float y0 = Rf[0] * X + Rf[1] * Y + Rf[2] * Z;
         const float y1 = Rf[3] * X + Rf[4] * Y + Rf[5] * Z;
         const float y2 = Rf[6] * X + Rf[7] * Y + Rf[8] * Z;
-        const float iz = 1.0f / (y2 + tf[2]);
+        const float iz = fast_rcpf(y2 + tf[2]);
         const float xn = (y0 + tf[0]) * iz, yn = (y1 + tf[1]) * iz;
         const float r2 = xn * xn + yn * yn, r4 = r2 * r2, r6 = r4 * r2;
         const float m = 1.0f + kf[4] * r2 + kf[5] * r4 + kf[8] * r6;

@@ -84,7 +84,7 @@ __device__ __forceinline__ void rig_geometry(const double (&Rf)[9], const double
   yc[0] = Rc[0] * p0 + Rc[1] * p1 + Rc[2] * p2;
   yc[1] = Rc[3] * p0 + Rc[4] * p1 + Rc[5] * p2;
   yc[2] = Rc[6] * p0 + Rc[7] * p1 + Rc[8] * p2;
-  const double iz = 1.0 / (yc[2] + tc[2]);
+  const double iz = fast_rcp(yc[2] + tc[2]);
   const double xn = (yc[0] + tc[0]) * iz, yn = (yc[1] + tc[1]) * iz;
   double ru = xn - mu, rv = yn - mv;
   const double s = ru * ru + rv * rv;
