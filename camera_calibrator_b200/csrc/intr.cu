@@ -661,6 +661,24 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
   s.solve_ok = 1;
 }
 
+// max |measurement| per problem (scale of the cost's rounding noise, lm_decide): one CTA per work
+// item, non-negative floats compared through their bit patterns
+__global__ void __launch_bounds__(256) k_intr_meas_scale(IntrDev d, unsigned* __restrict__ bits) {
+  const WorkItem it = d.items[blockIdx.x];
+  const int64_t o0 = d.view_off[it.v0], o1 = d.view_off[it.v1];
+  float m = 0.0f;
+  for (int64_t o = o0 + threadIdx.x; o < o1; o += blockDim.x)
+    m = fmaxf(m, fmaxf(fabsf(__ldg(d.u + o)), fabsf(__ldg(d.v + o))));
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0) atomicMax(bits + it.problem, __float_as_uint(m));
+}
+
+__global__ void k_intr_meas_finish(const unsigned* __restrict__ bits, double* __restrict__ out, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n) out[b] = (double)__uint_as_float(bits[b]);
+}
+
 __global__ void k_intr_init_state(IntrDev d, LmParams P, const double* intr0, const int2* item_ranges,
                                   const double* meas_scale, unsigned mask, int n_problems) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -832,15 +850,15 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_item_ranges, ranges.data(), sizeof(int2) * ranges.size(), cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_pose0, pose.data(), sizeof(double) * pose.size(), cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_intr0, intr, sizeof(double) * 9 * n_problems, cudaMemcpyHostToDevice, st));
-  // max |measurement| per problem: the scale of the cost's rounding noise (lm_decide)
-  std::vector<double> mscale((size_t)n_problems, 0.0);
-  for (int64_t b = 0; b < n_problems; ++b) {
-    float m = 0.0f;
-    for (int64_t o = view_offsets[problem_offsets[b]]; o < view_offsets[problem_offsets[b + 1]]; ++o)
-      m = std::max(m, std::max(std::fabs(u[o]), std::fabs(v[o])));
-    mscale[(size_t)b] = (double)m;
+  // max |measurement| per problem, computed on the device from the uploaded observations
+  {
+    unsigned* d_bits = nullptr;
+    CCG_TRY(dev_alloc(p, &d_bits, (size_t)n_problems));
+    CCG_CUDA(ctx, cudaMemsetAsync(d_bits, 0, sizeof(unsigned) * n_problems, st));
+    k_intr_meas_scale<<<p->n_items, 256, 0, st>>>(d, d_bits);
+    k_intr_meas_finish<<<(int)((n_problems + 127) / 128), 128, 0, st>>>(d_bits, p->d_meas_scale, (int)n_problems);
+    ctx->launches += 2;
   }
-  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_meas_scale, mscale.data(), sizeof(double) * n_problems, cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaStreamSynchronize(st));  // host staging vectors go out of scope
   return CCG_OK;
 }
