@@ -108,6 +108,7 @@ def lib():
         L.ccg_intrinsics_device_bytes.restype = C.c_int64
         L.ccg_intrinsics_device_bytes.argtypes = [C.c_void_p]
         L.ccg_destroy.argtypes = [C.c_void_p]
+        L.ccg_trim.argtypes = [C.c_void_p]
         L.ccg_intrinsics_destroy.argtypes = [C.c_void_p]
         if hasattr(L, "ccg_rig_destroy"):
             L.ccg_rig_destroy.argtypes = [C.c_void_p]

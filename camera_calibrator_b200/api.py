@@ -47,6 +47,10 @@ class Context:
                     "ccg_device_info")
         return dict(sm_count=sm.value, cc=(ma.value, mi.value), global_mem=mem.value)
 
+    def trim(self):
+        """Return the device memory cached from destroyed problems to the driver (ccg_trim)."""
+        self._check(_ccg.lib().ccg_trim(self._h), "ccg_trim")
+
     def kernel_launches(self) -> int:
         return int(_ccg.lib().ccg_kernel_launches(self._h))
 
@@ -112,7 +116,9 @@ class Context:
         self._check(rc, "ccg_intrinsics_solve_batch")
         return intr, q, t, [r.asdict() for r in reps]
 
-    def intrinsics_eval(self, u, v, X, Y, Z, view_offsets, intr, q, t, hessian_fp64=False):
+    def intrinsics_eval(self, u, v, X, Y, Z, view_offsets, intr, q, t, hessian_fp64=0):
+        """One sweep at the given point.  hessian_fp64: 0 tensor-core TF32 J'J (default sweep), 1 all FP64,
+        2 FP32 FFMA J'J (ccg_opts.hessian_fp64)."""
         u, v, X, Y, Z = map(f32, (u, v, X, Y, Z))
         off = i64(view_offsets)
         nv = len(off) - 1
@@ -132,7 +138,7 @@ class Context:
             ptr(Z, C.c_float), ptr(off, C.c_int64), C.c_int64(nv), ptr(intr, C.c_double),
             ptr(q, C.c_double), ptr(t, C.c_double), ptr(res, C.c_double), ptr(Vb, C.c_double),
             ptr(Wb, C.c_double), ptr(gv, C.c_double), ptr(U, C.c_double), ptr(gu, C.c_double),
-            ptr(cost, C.c_double), C.c_int(1 if hessian_fp64 else 0))
+            ptr(cost, C.c_double), C.c_int(int(hessian_fp64)))
         self._check(rc, "ccg_intrinsics_eval")
         return dict(res=res.reshape(n, 2), V=Vb, W=Wb, gv=gv, U=U, gu=gu, cost=float(cost[0]))
 

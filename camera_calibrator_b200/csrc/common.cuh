@@ -32,6 +32,9 @@ struct ccg_ctx {
   int* h_poll = nullptr;
   // event pool for opts.profile
   std::vector<cudaEvent_t> events;
+  // stream-ordered device memory pool: freed problem buffers stay cached for the next solve
+  // (cudaMalloc/cudaFree of the ~1 GB of a large calibration cost more than its whole LM loop)
+  cudaMemPool_t pool = nullptr;
 };
 
 namespace ccg {
@@ -45,6 +48,10 @@ int set_error(ccg_ctx* ctx, int status, const char* what, cudaError_t e = cudaSu
   } while (0)
 
 int nccl_allreduce_sum(ccg_ctx* ctx, double* buf, size_t count);
+
+// device memory from the context's pool, ordered on ctx->stream
+cudaError_t pool_alloc(ccg_ctx* ctx, void** out, size_t bytes);
+void pool_free(ccg_ctx* ctx, void* ptr);
 
 // --------------------------------------------------------------------------
 // LM state machine shared by the single-camera and the rig solver.  It lives

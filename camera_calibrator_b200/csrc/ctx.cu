@@ -68,6 +68,18 @@ int nccl_allreduce_sum(ccg_ctx* ctx, double* buf, size_t count) {
   return CCG_OK;
 }
 
+// ---------------------------------------------------------- memory pool ----
+cudaError_t pool_alloc(ccg_ctx* ctx, void** out, size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  if (!ctx->pool) return cudaMalloc(out, bytes);
+  return cudaMallocFromPoolAsync(out, bytes, ctx->pool, ctx->stream);
+}
+void pool_free(ccg_ctx* ctx, void* ptr) {
+  if (!ptr) return;
+  if (!ctx->pool) cudaFree(ptr);
+  else cudaFreeAsync(ptr, ctx->stream);
+}
+
 // ------------------------------------------------------------ profiler ----
 size_t Profiler::grab() {
   if (used == ctx->events.size()) {
@@ -187,6 +199,22 @@ int ccg_init(int device, ccg_ctx** out) {
     delete c;
     return CCG_ERR_CUDA;
   }
+  {
+    // private pool that never trims on synchronisation (ccg_trim releases it explicitly)
+    cudaMemPoolProps pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    if (cudaMemPoolCreate(&c->pool, &pp) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      c->pool = nullptr;  // plain cudaMalloc/cudaFree
+      cudaGetLastError();
+    }
+  }
   *out = c;
   return CCG_OK;
 }
@@ -197,8 +225,18 @@ void ccg_destroy(ccg_ctx* ctx) {
   if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+int ccg_trim(ccg_ctx* ctx) {
+  if (!ctx) return CCG_ERR_BAD_ARG;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->pool) CCG_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
+  return CCG_OK;
 }
 
 int ccg_device_info(ccg_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,

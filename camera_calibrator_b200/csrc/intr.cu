@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep(IntrDev d, double
 
 }  // namespace ccg
 #include "intr_mixed.cuh"
+#include "intr_tc.cuh"
 namespace ccg {
 
 // --------------------------------------------------------------------------
@@ -733,8 +735,8 @@ template <typename T>
 int dev_alloc(ccg_intr_problem* p, T** out, size_t n) {
   void* ptr = nullptr;
   const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-  cudaError_t e = cudaMalloc(&ptr, bytes);
-  if (e != cudaSuccess) return set_error(p->ctx, CCG_ERR_CUDA, "cudaMalloc", e);
+  cudaError_t e = pool_alloc(p->ctx, &ptr, bytes);
+  if (e != cudaSuccess) return set_error(p->ctx, CCG_ERR_CUDA, "device allocation", e);
   p->allocs.push_back(ptr);
   p->bytes += (int64_t)bytes;
   *out = (T*)ptr;
@@ -880,10 +882,40 @@ int reset_problem(ccg_intr_problem* p, const LmParams& P) {
 
 enum { TAG_SWEEP = 0, TAG_SCHUR = 1, TAG_SMALL = 2 };
 
+template <bool RES, int W>
+void launch_sweep_tc_w(ccg_intr_problem* p, double* res_out) {
+  static bool attr_set = false;  // per process; the attribute is per device function
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_intr_sweep_tc<RES, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(W));
+    attr_set = true;
+  }
+  k_intr_sweep_tc<RES, W><<<p->n_items, W * 32, tc_smem(W), p->ctx->stream>>>(p->dev, res_out);
+}
+
+void launch_sweep_tc(ccg_intr_problem* p, double* res_out) {
+  static int warps = 0;
+  if (!warps) {  // CCG_TC_WARPS: tuning knob (8, 12 or 16 warps per CTA)
+    const char* e = getenv("CCG_TC_WARPS");
+    warps = e ? atoi(e) : kTcWarps;
+    if (warps != 8 && warps != 12 && warps != 16) warps = kTcWarps;
+  }
+  if (res_out) {
+    launch_sweep_tc_w<true, kTcWarps>(p, res_out);
+  } else if (warps == 8) {
+    launch_sweep_tc_w<false, 8>(p, res_out);
+  } else if (warps == 16) {
+    launch_sweep_tc_w<false, 16>(p, res_out);
+  } else {
+    launch_sweep_tc_w<false, 12>(p, res_out);
+  }
+}
+
 // the sweep kernel variant: FP64 warp pairs, or mixed precision with G lanes per view
 void launch_sweep(ccg_intr_problem* p, const LmParams& P, double* res_out) {
   cudaStream_t st = p->ctx->stream;
-  if (P.hessian_fp64) {
+  if (P.hessian_fp64 == 0) {
+    launch_sweep_tc(p, res_out);
+  } else if (P.hessian_fp64 == 1) {
     k_intr_sweep<<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
   } else if (p->group == 8) {
     k_intr_sweep_mixed<8><<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
@@ -1053,7 +1085,7 @@ int download_problem(ccg_intr_problem* p, double* intr, double* q, double* t, cc
 void free_problem(ccg_intr_problem* p) {
   if (!p) return;
   if (p->ctx) cudaSetDevice(p->ctx->device);
-  for (void* a : p->allocs) cudaFree(a);
+  for (void* a : p->allocs) pool_free(p->ctx, a);
   delete p;
 }
 

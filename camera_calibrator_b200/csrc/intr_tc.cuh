@@ -1,0 +1,435 @@
+// Tensor-core single-camera sweep (included by intr.cu) - the default sweep kernel.
+//
+// Per observation the sweep needs (a) the residual, the cost and the gradient g = J'r, which
+// decide WHERE the LM iteration converges, and (b) the Gauss-Newton blocks V, W, U = J'J, which
+// only decide HOW FAST (a perturbed J'J still has g = 0 as its fixed point and every step is
+// validated against the FP64 cost).  (b) is 2/3 of the arithmetic and is a dense contraction:
+// per view  [V W; W' U] = sum over its 2P residual rows of (row)'(row), a 16 x 16 x 2P product.
+//   FP64 pipe  : forward model, residual, cost, and g_v / g_u by REVERSE mode (no explicit J)
+//   FP32 pipe  : a second forward pass and the analytic 2 x 15 Jacobian rows
+//   tensor pipe: J'J by mma.sync.m16n8k8 TF32 with FP32 accumulation - one lane owns one
+//                observation, writes its two Jacobian rows to a warp-private shared-memory tile,
+//                and the warp contracts 32 observations with 16 MMAs; the A fragment doubles as
+//                the B fragment (the product is J'J), so a k-step costs two LDS.64.
+// Operand precision: the raw float32 rows are fed to the TF32 unit (10 explicit mantissa bits).
+// tools/h_precision_study.py shows that the exact-Schur LM takes the same iterations with such
+// blocks and lands within 1e-10 of the all-FP64 solve (oracle experiment mode 311).
+// Why legacy mma.sync and not tcgen05: the tile is 16 x 16 per VIEW; tcgen05's smallest M is 64,
+// so four views would share an instruction through a block-diagonal A with 3/4 zeros, which makes
+// it slower per observation than mma.sync (measured 8.6 cycles per m16n8k8 per SM sub-partition,
+// tools/ubench_pipes.cu) while the kernel is bound by instruction issue, not by the tensor pipe.
+#pragma once
+
+namespace ccg {
+
+constexpr int kTcWarps = 12;       // default warps per CTA, one CTA per SM (168 registers per thread)
+constexpr int kTcRow = 20;         // floats per Jacobian row in the tile (16 + 4: conflict-free STS.128 and LDS.64)
+constexpr int kTcTile = 64 * kTcRow;  // one 32-observation tile; every warp owns two (double buffer)
+constexpr int kTcStages = 3;          // observation chunks in flight per warp (cp.async ring)
+constexpr int kTcStage = 5 * 32;      // floats per staged chunk: u v X Y Z of 32 observations
+constexpr size_t tc_smem(int warps) {
+  return sizeof(double) * warps * kSweepPart + sizeof(float) * warps * (2 * kTcTile + kTcStages * kTcStage);
+}
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], unsigned a0, unsigned a1, unsigned a2,
+                                                unsigned a3, unsigned b0, unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// destination of element (row, col) of the per-view 16 x 16 product inside the view block
+// (V21 | gv6 | W[:,fx fy px py] 24 | W[:,k1 k2 p1 p2 k3] 30), or -1.  Parameter order of the
+// product: 0..5 pose tangent, 6 fx, 7 fy, 8 px, 9 py, 10..14 k1 k2 p1 p2 k3, 15 unused.
+__device__ __forceinline__ int tc_blk_slot(int row, int col) {
+  if (row >= 6 || col < row || col >= 15) return -1;
+  if (col < 6) return row * 6 - row * (row - 1) / 2 + (col - row);
+  const int c = col - 6;
+  return c < 4 ? 27 + row * 4 + c : 51 + row * 5 + (c - 4);
+}
+
+// slot of U(row, col) in the per-item sweep partial (layout at the top of intr.cu), or -1 for the
+// lower triangle / structurally zero pairs.  row, col are product indices (6..14).
+__device__ __forceinline__ int tc_u_slot(int row, int col) {
+  if (row < 6 || col < row || col >= 15) return -1;
+  const int a = row - 6, b = col - 6;  // fx fy px py k1 k2 p1 p2 k3
+  if (b < 4) {
+    if (a == 0 && b == 0) return 1;
+    if (a == 0 && b == 2) return 2;
+    if (a == 2 && b == 2) return 3;
+    if (a == 1 && b == 1) return 4;
+    if (a == 1 && b == 3) return 5;
+    if (a == 3 && b == 3) return 6;
+    return -1;
+  }
+  const int c = b - 4;
+  if (a == 0) return 25 + c;
+  if (a == 2) return 30 + c;
+  if (a == 1) return 35 + c;
+  if (a == 3) return 40 + c;
+  const int e = a - 4;  // both distortion: packed upper triangle of the 5 x 5 block
+  return 45 + e * 5 - e * (e - 1) / 2 + (c - e);
+}
+
+// Per-CTA constants of the sweep (registers): intrinsics at the candidate point in both precisions.
+struct TcConst {
+  double fx, fy, cx, cy, k1, k2, p1, p2, k3;
+  float fxf, fyf, k1f, k2f, p1f, p2f, k3f;
+};
+
+// Per-view state: candidate pose in both precisions, the FP64 gradient accumulators.
+struct TcView {
+  double R[9], t[3];
+  float Rf[9], tf[3];
+  double gv[6];
+};
+
+// One observation per lane: FP64 residual / cost / gradients (accumulated into K-wide sums), and
+// the two float32 Jacobian rows in tile order.  Branch-free: an invalid lane (past the end of
+// the view) works on a clamped copy of the last observation with its residual, and every entry
+// of its rows, forced to zero.
+template <bool RES>
+__device__ __forceinline__ void tc_observation(const IntrDev& d, const TcConst& K, TcView& V, const ObsLoad& cur,
+                                               double (&gu)[9], double& cost, float4 (&ur)[4], float4 (&vr)[4],
+                                               double* __restrict__ res_out) {
+  // ================= FP64: forward, residual, cost, gradient by reverse mode =================
+  {
+    const double X = (double)cur.X, Y = (double)cur.Y, Z = (double)cur.Z;
+    const double pt0 = fma(V.R[0], X, fma(V.R[1], Y, fma(V.R[2], Z, V.t[0])));
+    const double pt1 = fma(V.R[3], X, fma(V.R[4], Y, fma(V.R[5], Z, V.t[1])));
+    const double pt2 = fma(V.R[6], X, fma(V.R[7], Y, fma(V.R[8], Z, V.t[2])));
+    const double iz = fast_rcp(pt2);
+    const double xn = pt0 * iz, yn = pt1 * iz;
+    const double xx = xn * xn, yy = yn * yn, xy = xn * yn;
+    const double r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
+    // m = 1 + k1 r2 + k2 r4 + k3 r6 and mp = dm/dr2 by Horner (no derived constants to keep in registers)
+    const double h2 = fma(r2, K.k3, K.k2), h1 = fma(r2, h2, K.k1);
+    const double m = fma(r2, h1, 1.0), mp = fma(r2, fma(r2, K.k3, h2), h1);
+    const double a1 = xy + xy, a2 = fma(2.0, xx, r2), a3 = fma(2.0, yy, r2);
+    const double xd = fma(xn, m, fma(K.p1, a1, K.p2 * a2));
+    const double yd = fma(yn, m, fma(K.p2, a1, K.p1 * a3));
+    double ru = fma(K.fx, xd, K.cx - (double)cur.mu);
+    double rv = fma(K.fy, yd, K.cy - (double)cur.mv);
+    ru = cur.valid ? ru : 0.0;
+    rv = cur.valid ? rv : 0.0;
+    if (RES) {
+      if (cur.valid) {
+        res_out[2 * (cur.o - d.obs_base)] = ru;
+        res_out[2 * (cur.o - d.obs_base) + 1] = rv;
+      }
+    }
+    cost = fma(ru, ru, fma(rv, rv, cost));
+    const double tu = K.fx * ru, tv = K.fy * rv;  // d cost / d(xd, yd)
+    gu[0] = fma(xd, ru, gu[0]);
+    gu[1] = fma(yd, rv, gu[1]);
+    gu[2] += ru;
+    gu[3] += rv;
+    const double sr = fma(xn, tu, yn * tv);
+    gu[4] = fma(r2, sr, gu[4]);
+    gu[5] = fma(r4, sr, gu[5]);
+    gu[8] = fma(r6, sr, gu[8]);
+    gu[6] = fma(a1, tu, fma(a3, tv, gu[6]));
+    gu[7] = fma(a2, tu, fma(a1, tv, gu[7]));
+    // d(xd,yd)/d(xn,yn): F00 = m + 2xx mp + 2p1 yn + 6p2 xn, F01 = a1 mp + 2p1 xn + 2p2 yn,
+    // F11 = m + 2yy mp + 2p2 xn + 6p1 yn
+    const double tx = xn + xn, ty = yn + yn;
+    const double u1 = K.p1 * ty, u2 = K.p2 * tx, base = m + (u1 + u2);
+    const double F00 = fma(2.0, u2, fma(a2 - r2, mp, base));
+    const double F01 = fma(a1, mp, fma(K.p1, tx, K.p2 * ty));
+    const double F11 = fma(2.0, u1, fma(a3 - r2, mp, base));
+    const double w0 = fma(F00, tu, F01 * tv) * iz, w1 = fma(F01, tu, F11 * tv) * iz;  // d cost / d(pt0, pt1)
+    const double w2 = -fma(xn, w0, yn * w1);                                          // d cost / d pt2
+    V.gv[3] += w0;
+    V.gv[4] += w1;
+    V.gv[5] += w2;
+    // rotation tangent: 2 (y x w) with y = pt - t; accumulated as pt x w, fixed up per view
+    V.gv[0] = fma(pt1, w2, fma(-pt2, w1, V.gv[0]));
+    V.gv[1] = fma(pt2, w0, fma(-pt0, w2, V.gv[1]));
+    V.gv[2] = fma(pt0, w1, fma(-pt1, w0, V.gv[2]));
+  }
+  // ================= FP32: the two Jacobian rows =================
+  {
+    const float one = cur.valid ? 1.0f : 0.0f;
+    const float fxv = cur.valid ? K.fxf : 0.0f, fyv = cur.valid ? K.fyf : 0.0f;
+    const float X = cur.X, Y = cur.Y, Z = cur.Z;
+    const float y0 = fmaf(V.Rf[0], X, fmaf(V.Rf[1], Y, V.Rf[2] * Z));
+    const float y1 = fmaf(V.Rf[3], X, fmaf(V.Rf[4], Y, V.Rf[5] * Z));
+    const float y2 = fmaf(V.Rf[6], X, fmaf(V.Rf[7], Y, V.Rf[8] * Z));
+    const float iz = fast_rcpf(y2 + V.tf[2]);
+    const float xn = (y0 + V.tf[0]) * iz, yn = (y1 + V.tf[1]) * iz;
+    const float xx = xn * xn, yy = yn * yn, xy = xn * yn;
+    const float r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
+    const float h2 = fmaf(r2, K.k3f, K.k2f), h1 = fmaf(r2, h2, K.k1f);
+    const float m = fmaf(r2, h1, 1.0f), mp = fmaf(r2, fmaf(r2, K.k3f, h2), h1);
+    const float a1 = xy + xy, a2 = fmaf(2.0f, xx, r2), a3 = fmaf(2.0f, yy, r2);
+    const float xd = fmaf(xn, m, fmaf(K.p1f, a1, K.p2f * a2));
+    const float yd = fmaf(yn, m, fmaf(K.p2f, a1, K.p1f * a3));
+    const float tx = xn + xn, ty = yn + yn;
+    const float u1 = K.p1f * ty, u2 = K.p2f * tx, base = m + (u1 + u2);
+    const float F00 = fmaf(2.0f, u2, fmaf(a2 - r2, mp, base));
+    const float F01 = fmaf(a1, mp, fmaf(K.p1f, tx, K.p2f * ty));
+    const float F11 = fmaf(2.0f, u1, fmaf(a3 - r2, mp, base));
+    const float fiz = fxv * iz, giz = fyv * iz;
+    // d(u,v)/d(camera point): rows (A0 A1 A2), (B0 B1 B2)
+    const float A0 = fiz * F00, A1 = fiz * F01, B0 = giz * F01, B1 = giz * F11;
+    const float A2 = -fmaf(A0, xn, A1 * yn), B2 = -fmaf(B0, xn, B1 * yn);
+    // d(camera point)/d(rotation tangent) = 2 (y x .)
+    const float z0 = y0 + y0, z1 = y1 + y1, z2 = y2 + y2;
+    const float ju0 = fmaf(z1, A2, -z2 * A1), ju1 = fmaf(z2, A0, -z0 * A2), ju2 = fmaf(z0, A1, -z1 * A0);
+    const float jv0 = fmaf(z1, B2, -z2 * B1), jv1 = fmaf(z2, B0, -z0 * B2), jv2 = fmaf(z0, B1, -z1 * B0);
+    const float fxn = fxv * xn, fyn = fyv * yn;
+    // tile order of a row: product column m sits at position (m % 8) * 2 + m / 8, so one
+    // LDS.64 at float 2g returns columns g and g + 8:
+    //   [c0 c8 | c1 c9 | c2 c10 | c3 c11 | c4 c12 | c5 c13 | c6 c14 | c7 c15]
+    // u row: c0..5 pose, c6 = xd (fx), c7 = 0 (fy), c8 = 1 (px), c9 = 0 (py), c10..14 = k1 k2 p1 p2 k3
+    ur[0] = make_float4(ju0, one, ju1, 0.0f);
+    ur[1] = make_float4(ju2, fxn * r2, A0, fxn * r4);
+    ur[2] = make_float4(A1, fxv * a1, A2, fxv * a2);
+    ur[3] = make_float4(xd * one, fxn * r6, 0.0f, 0.0f);
+    // v row: c6 = 0, c7 = yd (fy), c8 = 0, c9 = 1 (py)
+    vr[0] = make_float4(jv0, 0.0f, jv1, one);
+    vr[1] = make_float4(jv2, fyn * r2, B0, fyn * r4);
+    vr[2] = make_float4(B1, fyv * a3, B2, fyv * a1);
+    vr[3] = make_float4(0.0f, fyn * r6, yd * one, 0.0f);
+  }
+}
+
+// rows 0..31 of a tile = u rows of the 32 observations, rows 32..63 = their v rows
+__device__ __forceinline__ void tc_store_rows(float* tile, int lane, const float4 (&ur)[4], const float4 (&vr)[4]) {
+  float4* tu4 = reinterpret_cast<float4*>(tile + lane * kTcRow);
+  float4* tv4 = reinterpret_cast<float4*>(tile + (32 + lane) * kTcRow);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    tu4[i] = ur[i];
+    tv4[i] = vr[i];
+  }
+}
+
+// [V W; W' U] += rows' rows over one tile.  k-step s contracts tile rows 8s..8s+7 (k = tig -> row
+// 8s + 2 tig, k = tig + 4 -> the next row); two accumulator sets per column block halve the
+// depth of the dependent HMMA chain.  FULL: all 32 observations are valid.
+template <bool FULL>
+__device__ __forceinline__ void tc_contract(const float* tile, int g, int tig, int nvalid, float (&c0a)[4],
+                                            float (&c0b)[4], float (&c1a)[4], float (&c1b)[4]) {
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    if (FULL || 8 * (s & 3) < nvalid) {
+      const float2 lo = *reinterpret_cast<const float2*>(tile + (8 * s + 2 * tig) * kTcRow + 2 * g);
+      const float2 hi = *reinterpret_cast<const float2*>(tile + (8 * s + 2 * tig + 1) * kTcRow + 2 * g);
+      const unsigned a0 = __float_as_uint(lo.x), a1 = __float_as_uint(lo.y);
+      const unsigned a2 = __float_as_uint(hi.x), a3 = __float_as_uint(hi.y);
+      if (s & 1) {
+        mma_tf32_16x8x8(c0b, a0, a1, a2, a3, a0, a2);
+        mma_tf32_16x8x8(c1b, a0, a1, a2, a3, a1, a3);
+      } else {
+        mma_tf32_16x8x8(c0a, a0, a1, a2, a3, a0, a2);
+        mma_tf32_16x8x8(c1a, a0, a1, a2, a3, a1, a3);
+      }
+    }
+  }
+}
+
+// Asynchronous prefetch of one 32-observation chunk into the warp's staging ring (LDGSTS: no
+// registers are held while the loads are in flight, so ptxas cannot sink them next to their use -
+// it did exactly that with plain prefetch loads).  Lanes past the end of the view zero-fill.
+__device__ __forceinline__ void tc_prefetch(float* stage, const IntrDev& d, int64_t idx, int64_t end, int lane) {
+  const bool valid = idx < end;
+  const int64_t o = valid ? idx : 0;
+  const int sz = valid ? 4 : 0;
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + lane);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(d.u + o), "r"(sz) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128), "l"(d.v + o), "r"(sz) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 256), "l"(d.X + o), "r"(sz) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 384), "l"(d.Y + o), "r"(sz) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 512), "l"(d.Z + o), "r"(sz) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// wait until at most kTcStages - 1 younger groups are pending, then read this lane's observation
+__device__ __forceinline__ void tc_take(ObsLoad& L, const float* stage, int64_t idx, int64_t end, int lane) {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kTcStages - 1) : "memory");
+  L.valid = idx < end;
+  L.o = idx;
+  L.mu = stage[lane];
+  L.mv = stage[32 + lane];
+  L.X = stage[64 + lane];
+  L.Y = stage[96 + lane];
+  L.Z = stage[128 + lane];
+}
+
+template <bool RES, int kTcWarps>
+__global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, double* __restrict__ res_out) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];  // kTcSmem bytes: partials, then the tiles
+  double(*s_part)[kSweepPart] = reinterpret_cast<double(*)[kSweepPart]>(s_dyn);
+  float* s_tiles = reinterpret_cast<float*>(s_dyn + sizeof(double) * kTcWarps * kSweepPart);
+  __shared__ double s_k[9], s_du[9];
+  __shared__ int s_meta[2];
+  const WorkItem it = d.items[blockIdx.x];
+  IntrState& ps = d.ps[it.problem];
+  if (threadIdx.x == 0) {
+    s_meta[0] = ps.lm.par;
+    s_meta[1] = (ps.lm.status == 0 && ps.lm.solve_ok) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_meta[1]) return;
+  const int par = s_meta[0];
+  if (threadIdx.x < 9) {
+    s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
+    s_du[threadIdx.x] = ps.du[threadIdx.x];
+  }
+  for (int i = threadIdx.x; i < kTcWarps * kSweepPart; i += blockDim.x) (&s_part[0][0])[i] = 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  float* tiles = s_tiles + warp * (2 * kTcTile + kTcStages * kTcStage);
+  float* stages = tiles + 2 * kTcTile;
+  double* upart = s_part[warp];
+
+  TcConst K;
+  K.fx = s_k[0]; K.fy = s_k[1]; K.cx = s_k[2]; K.cy = s_k[3];
+  K.k1 = s_k[4]; K.k2 = s_k[5]; K.p1 = s_k[6]; K.p2 = s_k[7]; K.k3 = s_k[8];
+  K.fxf = (float)K.fx; K.fyf = (float)K.fy;
+  K.k1f = (float)K.k1; K.k2f = (float)K.k2; K.p1f = (float)K.p1; K.p2f = (float)K.p2; K.k3f = (float)K.k3;
+  // opaque: keeps ptxas from re-converting the constants per observation (F2F runs at 1/8 rate)
+  asm volatile("" : "+f"(K.fxf), "+f"(K.fyf), "+f"(K.k1f), "+f"(K.k2f), "+f"(K.p1f), "+f"(K.p2f), "+f"(K.k3f));
+
+  double gu[9], cost = 0.0, gTd = 0.0, dDd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gu[i] = 0.0;
+
+  for (int64_t v = it.v0 + warp; v < it.v1; v += kTcWarps) {
+    // the first chunks of the view stream in while the candidate pose is being formed
+    const int64_t o0 = d.view_off[v], o1 = d.view_off[v + 1];
+    tc_prefetch(stages, d, o0 + lane, o1, lane);
+    tc_prefetch(stages + kTcStage, d, o0 + 32 + lane, o1, lane);
+    // ---------------- candidate pose of the view: current (+) (-z - Y du)
+    TcView V;
+    {
+      double dl = 0.0;
+      const double* yz = d.yz + (size_t)v * kYz;
+      if (lane < 6) {
+        dl = -yz[54 + lane];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) dl -= yz[lane * 9 + j] * s_du[j];
+        gTd += yz[60 + lane] * dl;
+        dDd += dl * dl * yz[66 + lane];
+      }
+      const double d0 = __shfl_sync(0xffffffffu, dl, 0), d1 = __shfl_sync(0xffffffffu, dl, 1),
+                   d2 = __shfl_sync(0xffffffffu, dl, 2), d3 = __shfl_sync(0xffffffffu, dl, 3),
+                   d4 = __shfl_sync(0xffffffffu, dl, 4), d5 = __shfl_sync(0xffffffffu, dl, 5);
+      const double* pc = d.pose[par] + (size_t)v * kPose;
+      double q[4] = {pc[0], pc[1], pc[2], pc[3]};
+      double qn[4];
+      quat_plus(q, d0, d1, d2, qn);
+      V.t[0] = pc[4] + d3;
+      V.t[1] = pc[5] + d4;
+      V.t[2] = pc[6] + d5;
+      if (lane < 7) {
+        double* pn = d.pose[par ^ 1] + (size_t)v * kPose;
+        const double val = lane == 0 ? qn[0] : lane == 1 ? qn[1] : lane == 2 ? qn[2] : lane == 3 ? qn[3]
+                         : lane == 4 ? V.t[0] : lane == 5 ? V.t[1] : V.t[2];
+        pn[lane] = val;
+      }
+      quat_to_rot(qn, V.R);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      V.Rf[i] = (float)V.R[i];
+      asm volatile("" : "+f"(V.Rf[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      V.tf[i] = (float)V.t[i];
+      asm volatile("" : "+f"(V.tf[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) V.gv[i] = 0.0;
+    // product columns 0..7 (c0*) and 8..15 (c1*), two accumulator sets each
+    float c0a[4] = {0.f, 0.f, 0.f, 0.f}, c0b[4] = {0.f, 0.f, 0.f, 0.f};
+    float c1a[4] = {0.f, 0.f, 0.f, 0.f}, c1b[4] = {0.f, 0.f, 0.f, 0.f};
+
+    if (o1 > o0) {
+      // software pipeline over 32-observation chunks: while chunk j's rows are being computed
+      // (FP64 + FP32 pipes), chunk j-1's tile is contracted (LDS + tensor pipe) and chunk j+2 is
+      // in flight from HBM; the streams are independent inside one loop body
+      ObsLoad cur;
+      float4 ur[4], vr[4];
+      tc_prefetch(stages + 2 * kTcStage, d, o0 + 64 + lane, o1, lane);
+      tc_take(cur, stages, o0 + lane, o1, lane);
+      tc_observation<RES>(d, K, V, cur, gu, cost, ur, vr, res_out);
+      tc_store_rows(tiles, lane, ur, vr);
+      __syncwarp();
+      int buf = 0, st = 1;  // tile that holds chunk j-1, stage that holds chunk j
+      int64_t ob = o0 + 32;
+      for (; ob < o1; ob += 32) {
+        const int st_free = st == 0 ? kTcStages - 1 : st - 1;  // chunk j-1's stage: consumed
+        tc_prefetch(stages + st_free * kTcStage, d, ob + 64 + lane, o1, lane);
+        tc_take(cur, stages + st * kTcStage, ob + lane, o1, lane);
+        tc_contract<true>(tiles + buf * kTcTile, g, tig, 32, c0a, c0b, c1a, c1b);
+        tc_observation<RES>(d, K, V, cur, gu, cost, ur, vr, res_out);
+        buf ^= 1;
+        st = st == kTcStages - 1 ? 0 : st + 1;
+        tc_store_rows(tiles + buf * kTcTile, lane, ur, vr);
+        __syncwarp();
+      }
+      tc_contract<false>(tiles + buf * kTcTile, g, tig, (int)(o1 - (ob - 32)), c0a, c0b, c1a, c1b);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---------------- per-view epilogue: blocks, gradient, U contribution
+    double* blk = d.blk[par ^ 1] + (size_t)v * kBlk;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int nt = i >> 2, e = i & 3;
+      const int row = g + ((e & 2) ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
+      const float val = nt == 0 ? c0a[e] + c0b[e] : c1a[e] + c1b[e];
+      const int bs = tc_blk_slot(row, col), us = tc_u_slot(row, col);
+      if (bs >= 0) blk[bs] = (double)val;
+      if (us >= 0) upart[us] += (double)val;  // one owner lane per slot within the warp
+    }
+    {
+      double tmp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tmp[i] = i < 6 ? V.gv[i] : 0.0;
+      double r = group_reduce<8, double>(tmp, lane & 7);
+      r += __shfl_xor_sync(0xffffffffu, r, 8);
+      r += __shfl_xor_sync(0xffffffffu, r, 16);
+      // lanes 0..5 hold sum(pt x w) (0..2) and sum(w) (3..5); y x w = pt x w - t x sum(w)
+      const double sw0 = __shfl_sync(0xffffffffu, r, 3), sw1 = __shfl_sync(0xffffffffu, r, 4),
+                   sw2 = __shfl_sync(0xffffffffu, r, 5);
+      double out = r;
+      if (lane == 0) out = 2.0 * (r - (V.t[1] * sw2 - V.t[2] * sw1));
+      if (lane == 1) out = 2.0 * (r - (V.t[2] * sw0 - V.t[0] * sw2));
+      if (lane == 2) out = 2.0 * (r - (V.t[0] * sw1 - V.t[1] * sw0));
+      if (lane < 6) blk[21 + lane] = out;
+    }
+  }
+  // ---------------- end of item: lane-private sums -> warp partial -> one partial per CTA
+  {
+    // partial layout: [0] sum r^2 | [7] g'd | [8] d'Dd | [16..24] g_u (U slots were filled per view)
+    double tmp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tmp[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tmp[i] = gu[i];
+    tmp[9] = cost;
+    tmp[10] = gTd;
+    tmp[11] = dDd;
+    double r = group_reduce<16, double>(tmp, lane & 15);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    if (lane < 9) upart[16 + lane] = r;
+    else if (lane == 9) upart[0] = r;
+    else if (lane == 10) upart[7] = r;
+    else if (lane == 11) upart[8] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < kSweepPart) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTcWarps; ++w) s += s_part[w][threadIdx.x];
+    d.sweep_part[(size_t)blockIdx.x * kSweepPart + threadIdx.x] = s;
+  }
+}
+
+}  // namespace ccg

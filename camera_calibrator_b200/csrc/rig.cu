@@ -634,8 +634,8 @@ namespace {
 template <typename T>
 int rig_alloc(ccg_rig_problem* p, T** out, size_t n) {
   void* ptr = nullptr;
-  cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(n, 1) * sizeof(T));
-  if (e != cudaSuccess) return set_error(p->ctx, CCG_ERR_CUDA, "cudaMalloc", e);
+  cudaError_t e = pool_alloc(p->ctx, &ptr, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return set_error(p->ctx, CCG_ERR_CUDA, "device allocation", e);
   p->allocs.push_back(ptr);
   *out = (T*)ptr;
   return CCG_OK;
@@ -644,7 +644,7 @@ int rig_alloc(ccg_rig_problem* p, T** out, size_t n) {
 void rig_free(ccg_rig_problem* p) {
   if (!p) return;
   if (p->ctx) cudaSetDevice(p->ctx->device);
-  for (void* a : p->allocs) cudaFree(a);
+  for (void* a : p->allocs) pool_free(p->ctx, a);
   delete p;
 }
 
@@ -885,13 +885,13 @@ int rig_download(ccg_rig_problem* p, double* q_c, double* t_c, double* q_f, doub
   if (obs_cost && p->n_obs > 0) {
     // per-observation 0.5*rho at the returned point (extrinsics_calibrator.cpp:219-225)
     double* d_cost = nullptr;
-    CCG_CUDA(ctx, cudaMalloc(&d_cost, sizeof(double) * p->n_obs));
+    CCG_CUDA(ctx, pool_alloc(ctx, (void**)&d_cost, sizeof(double) * p->n_obs));
     k_rig_sweep<<<p->n_items, kRigWarps * 32, 0, ctx->stream>>>(p->dev, p->huber_a, nullptr, d_cost);
     ctx->launches++;
     std::vector<double> sorted((size_t)p->n_obs);
     cudaError_t e = cudaMemcpyAsync(sorted.data(), d_cost, sizeof(double) * p->n_obs, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_cost);
+    pool_free(ctx, d_cost);
     if (e != cudaSuccess) return set_error(ctx, CCG_ERR_CUDA, "obs cost", e);
     for (int64_t i = 0; i < p->n_obs; ++i) obs_cost[p->perm[(size_t)i]] = sorted[(size_t)i];
   }

@@ -52,8 +52,10 @@ typedef struct {
   double huber_a;               /* rig only: (double)(3.0f/500.0f), extrinsics_calibrator.cpp:176; <= 0: no loss */
   double noise_factor;          /* 4: a step whose predicted decrease is <= noise_factor * (eps/2) * max|measurement| *
                                    sqrt(2 cost) is below the FP64 resolution of the cost: take it and stop */
-  int32_t hessian_fp64;         /* 0 (default): single-camera sweep forms J'J in FP32 (residual, cost and gradient stay
-                                   FP64; same fixed point); 1: everything in FP64 */
+  int32_t hessian_fp64;         /* single-camera sweep variant.  Residual, cost and gradient are FP64 in all of them (same
+                                   fixed point); they differ in how the J'J blocks are formed:
+                                   0 (default) TF32 tensor-core products of float32 Jacobian rows, 1 everything in
+                                   FP64, 2 float32 FFMA products */
   int32_t reserved_;
 } ccg_opts;
 
@@ -92,6 +94,9 @@ const char* ccg_last_error(const ccg_ctx* ctx);
 /* device = CUDA ordinal this context binds to (one context per GPU / rank). */
 int ccg_init(int device, ccg_ctx** out);
 void ccg_destroy(ccg_ctx* ctx);
+/* Device buffers of destroyed problems stay cached in the context's memory pool (a second
+ * solve of the same size allocates nothing); ccg_trim returns the cached memory to the driver. */
+int ccg_trim(ccg_ctx* ctx);
 int ccg_device_info(ccg_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
                     int64_t* global_mem_bytes);
 

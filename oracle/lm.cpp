@@ -157,6 +157,36 @@ static void eval_single(const SingleData& D, const double* intr, const double* q
           float Jif[9], Jpf[6];
           for (int a = 0; a < 9; ++a) Jif[a] = (float)Ji[a] * (g_h_float == 2 ? (1.0f + 1e-6f * ((a * 7 + row) % 3 - 1)) : 1.0f);
           for (int a = 0; a < 6; ++a) Jpf[a] = (float)Jp[a] * (g_h_float == 2 ? (1.0f + 1e-6f * ((a * 5 + row) % 3 - 1)) : 1.0f);
+          if (g_h_float >= 100) {
+            // EXPERIMENT (modes 1BB / 2BB): the J'J products as a split low-precision tensor-core
+            // contraction would form them.  Every Jacobian entry x = h + l with h, l rounded to BB
+            // significant bits (8 = bfloat16, 11 = tf32 / half); mode 1BB accumulates hh + hl + lh
+            // (two-pass split, ll dropped), modes 2BB / 3BB only hh (single pass); float32 accumulation.
+            const int bits = g_h_float % 100;
+            const bool two = g_h_float < 200;
+            const bool trunc = g_h_float >= 300;  // mode 3BB: single pass, operands truncated (what
+                                                  // mma .tf32 does to raw float32 bits)
+            auto rnd = [bits, trunc](float x) {
+              if (x == 0.0f) return 0.0f;
+              int e;
+              const float m = std::ldexp(std::frexp(x, &e), bits);
+              return std::ldexp(trunc ? std::trunc(m) : std::nearbyint(m), e - bits);
+            };
+            float hi[15], lo[15];
+            for (int a = 0; a < 6; ++a) { hi[a] = rnd(Jpf[a]); lo[a] = two ? rnd(Jpf[a] - hi[a]) : 0.0f; }
+            for (int a = 0; a < 9; ++a) { hi[6 + a] = rnd(Jif[a]); lo[6 + a] = two ? rnd(Jif[a] - hi[6 + a]) : 0.0f; }
+            auto prod = [&](int a, int b) { return hi[a] * hi[b] + (hi[a] * lo[b] + lo[a] * hi[b]); };
+            for (int a = 0; a < 9; ++a) {
+              guv[a] += Ji[a] * rr;
+              for (int b = 0; b < 9; ++b) Uf[a * 9 + b] += prod(6 + a, 6 + b);
+            }
+            for (int a = 0; a < 6; ++a) {
+              gvv[a] += Jp[a] * rr;
+              for (int b = 0; b < 6; ++b) Vf[a * 6 + b] += prod(a, b);
+              for (int b = 0; b < 9; ++b) Wf[a * 9 + b] += prod(a, 6 + b);
+            }
+            continue;
+          }
           for (int a = 0; a < 9; ++a) {
             guv[a] += Ji[a] * rr;
             for (int b = 0; b < 9; ++b) Uf[a * 9 + b] += Jif[a] * Jif[b];
