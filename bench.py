@@ -40,10 +40,12 @@ WORKLOADS = {
     "c4": (50, 54, 4096),
     "c5": (100000, 400, 1),
 }
-# per observation per sweep of the default (mixed-precision) sweep kernel, counted in its SASS loop
-# body: 56 DFMA + 28 DMUL + 19 DADD and 192 FFMA + 48 FMUL + 38 FADD
-FP64_FLOP_PER_OBS = 159.0
-FP32_FLOP_PER_OBS = 470.0
+# per observation per sweep of the default (warp-specialised tensor-core) sweep kernel, counted in
+# the SASS loop bodies of its two roles: FP64 role 54 DFMA + 20 DMUL + 14 DADD,
+# Jacobian role 32 FFMA + 43 FMUL + 15 FADD, and 16 HMMA.1688.TF32 (m16n8k8) per 32 observations
+FP64_FLOP_PER_OBS = 142.0
+FP32_FLOP_PER_OBS = 122.0
+TF32_FLOP_PER_OBS = 16 * 2.0 * 16 * 8 * 8 / 32.0
 
 
 def algorithmic_bytes(n_obs, n_views):
@@ -380,7 +382,7 @@ def run_ours(args):
             "breakdown_ms_per_step": {"sweep": sweep_ms / args.steps, "eliminate": schur_ms / args.steps,
                                       "reduce+decide+solve(+allreduce)": small_ms / args.steps,
                                       "allreduces_per_step": n_allreduce / args.steps},
-            "roofline": {"kernel": "k_intr_sweep_mixed", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"kernel": "k_intr_sweep_tc (+ k_intr_step, timed together)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src, "launch_ms": sweep_ms_avg, "launches": n_sweeps,
                          "algorithmic_bytes_per_launch": alg_bytes,
@@ -388,7 +390,9 @@ def run_ours(args):
                                   "peak_tflops": fp64_peak, "flop_per_obs": FP64_FLOP_PER_OBS,
                                   "peak_source": "DFMA micro-benchmark run in this process"},
                          "fp32": {"achieved_tflops": FP32_FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
-                                  "flop_per_obs": FP32_FLOP_PER_OBS}},
+                                  "flop_per_obs": FP32_FLOP_PER_OBS},
+                         "tf32_mma": {"achieved_tflops": TF32_FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
+                                      "flop_per_obs": TF32_FLOP_PER_OBS}},
             "cpu_baseline": {"value": cpu_v, "unit": "obs/s", "cores": oracle.num_threads(), "kind": "port",
                              "sample": sample[5], "seconds": cpu_dt},
             "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": int(allsum(float(h2d))) if world > 1 else int(h2d),

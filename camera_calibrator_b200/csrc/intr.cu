@@ -60,6 +60,8 @@ struct IntrDev {
   double* pose[2];
   double* blk[2];
   double* yz;
+  double* rt;         // candidate pose as rotation matrix + translation, 12 doubles per view (tensor-core sweep)
+  double* step_part;  // g'd, d'Dd partials of the candidate-pose kernel: [item * schur_split + sub][2]
   double* sweep_part;
   double* schur_part;
   double* red_sweep;  // [B][64]
@@ -818,6 +820,8 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   for (const WorkItem& w : items) max_item_views = std::max<int64_t>(max_item_views, w.v1 - w.v0);
   const int schur_split = (int)std::max<int64_t>(1, std::min<int64_t>((max_item_views + 127) / 128, 16));
   CCG_TRY(dev_alloc(p, &d.schur_part, items.size() * (size_t)schur_split * kSchurPart));
+  CCG_TRY(dev_alloc(p, &d.rt, (size_t)n_views * 12));
+  CCG_TRY(dev_alloc(p, &d.step_part, items.size() * (size_t)schur_split * 2));
   CCG_TRY(dev_alloc(p, &d.red_sweep, (size_t)n_problems * kSweepPart));
   CCG_TRY(dev_alloc(p, &d.red_schur, (size_t)n_problems * kSchurPart));
   CCG_TRY(dev_alloc(p, &d.ps, (size_t)n_problems));
@@ -882,32 +886,22 @@ int reset_problem(ccg_intr_problem* p, const LmParams& P) {
 
 enum { TAG_SWEEP = 0, TAG_SCHUR = 1, TAG_SMALL = 2 };
 
-template <bool RES, int W>
-void launch_sweep_tc_w(ccg_intr_problem* p, double* res_out) {
+template <bool RES>
+void launch_sweep_tc_t(ccg_intr_problem* p, double* res_out) {
   static bool attr_set = false;  // per process; the attribute is per device function
   if (!attr_set) {
-    cudaFuncSetAttribute(k_intr_sweep_tc<RES, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(W));
+    cudaFuncSetAttribute(k_intr_sweep_tc<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
     attr_set = true;
   }
-  k_intr_sweep_tc<RES, W><<<p->n_items, W * 32, tc_smem(W), p->ctx->stream>>>(p->dev, res_out);
+  k_intr_sweep_tc<RES><<<p->n_items, kTcWarps * 32, kTcSmem, p->ctx->stream>>>(p->dev, res_out);
 }
 
+// candidate poses (back-substitution), then the warp-specialised sweep
 void launch_sweep_tc(ccg_intr_problem* p, double* res_out) {
-  static int warps = 0;
-  if (!warps) {  // CCG_TC_WARPS: tuning knob (8, 12 or 16 warps per CTA)
-    const char* e = getenv("CCG_TC_WARPS");
-    warps = e ? atoi(e) : kTcWarps;
-    if (warps != 8 && warps != 12 && warps != 16) warps = kTcWarps;
-  }
-  if (res_out) {
-    launch_sweep_tc_w<true, kTcWarps>(p, res_out);
-  } else if (warps == 8) {
-    launch_sweep_tc_w<false, 8>(p, res_out);
-  } else if (warps == 16) {
-    launch_sweep_tc_w<false, 16>(p, res_out);
-  } else {
-    launch_sweep_tc_w<false, 12>(p, res_out);
-  }
+  k_intr_step<<<p->n_items * p->dev.schur_split, kStepThreads, 0, p->ctx->stream>>>(p->dev);
+  p->ctx->launches++;
+  if (res_out) launch_sweep_tc_t<true>(p, res_out);
+  else launch_sweep_tc_t<false>(p, res_out);
 }
 
 // the sweep kernel variant: FP64 warp pairs, or mixed precision with G lanes per view

@@ -1,4 +1,4 @@
-// Tensor-core single-camera sweep (included by intr.cu) - the default sweep kernel.
+// Warp-specialised tensor-core single-camera sweep (included by intr.cu) - the default sweep.
 //
 // Per observation the sweep needs (a) the residual, the cost and the gradient g = J'r, which
 // decide WHERE the LM iteration converges, and (b) the Gauss-Newton blocks V, W, U = J'J, which
@@ -22,14 +22,24 @@
 
 namespace ccg {
 
-constexpr int kTcWarps = 12;       // default warps per CTA, one CTA per SM (168 registers per thread)
+#ifndef CCG_TC_WARPS
+#define CCG_TC_WARPS 16
+#endif
+constexpr int kTcWarps = CCG_TC_WARPS;  // warps per CTA, one CTA per SM
+#ifndef CCG_TC_D
+#define CCG_TC_D (kTcWarps / 2)
+#endif
+constexpr int kTcD = CCG_TC_D;     // FP64-role warps (the first kTcD warps of the CTA)
+constexpr int kTcJ = kTcWarps - kTcD;  // Jacobian/tensor-role warps
 constexpr int kTcRow = 20;         // floats per Jacobian row in the tile (16 + 4: conflict-free STS.128 and LDS.64)
 constexpr int kTcTile = 64 * kTcRow;  // one 32-observation tile; every warp owns two (double buffer)
 constexpr int kTcStages = 3;          // observation chunks in flight per warp (cp.async ring)
 constexpr int kTcStage = 5 * 32;      // floats per staged chunk: u v X Y Z of 32 observations
-constexpr size_t tc_smem(int warps) {
-  return sizeof(double) * warps * kSweepPart + sizeof(float) * warps * (2 * kTcTile + kTcStages * kTcStage);
-}
+constexpr int kTcRing = kTcStages * kTcStage;  // floats per warp: the observation ring
+// dynamic shared memory: per warp a 64-double partial and a 3-stage observation ring; per
+// Jacobian warp two tiles
+constexpr size_t kTcSmem = sizeof(double) * kTcWarps * kSweepPart +
+                           sizeof(float) * (kTcWarps * kTcRing + kTcJ * 2 * kTcTile);
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], unsigned a0, unsigned a1, unsigned a2,
                                                 unsigned a3, unsigned b0, unsigned b1) {
@@ -72,127 +82,132 @@ __device__ __forceinline__ int tc_u_slot(int row, int col) {
   return 45 + e * 5 - e * (e - 1) / 2 + (c - e);
 }
 
-// Per-CTA constants of the sweep (registers): intrinsics at the candidate point in both precisions.
-struct TcConst {
+// Per-CTA constants of the sweep (registers): intrinsics at the candidate point.
+struct TcConst64 {
   double fx, fy, cx, cy, k1, k2, p1, p2, k3;
-  float fxf, fyf, k1f, k2f, p1f, p2f, k3f;
+};
+struct TcConst32 {
+  float fx, fy, k1, k2, p1, p2, k3;
 };
 
-// Per-view state: candidate pose in both precisions, the FP64 gradient accumulators.
-struct TcView {
-  double R[9], t[3];
-  float Rf[9], tf[3];
-  double gv[6];
+struct ObsIn {
+  float mu, mv, X, Y, Z;
+  int64_t o;
+  bool valid;
 };
 
-// One observation per lane: FP64 residual / cost / gradients (accumulated into K-wide sums), and
-// the two float32 Jacobian rows in tile order.  Branch-free: an invalid lane (past the end of
-// the view) works on a clamped copy of the last observation with its residual, and every entry
-// of its rows, forced to zero.
+// ---------------------------------------------------------------------------------------------
+// FP64 role: forward model, residual, cost, and the gradients g_u / g_v by reverse mode, one
+// observation per lane.  Branch-free: an invalid lane (past the end of the view) sees a
+// zero-filled observation and its residual is forced to zero, so it contributes nothing.
+// ---------------------------------------------------------------------------------------------
 template <bool RES>
-__device__ __forceinline__ void tc_observation(const IntrDev& d, const TcConst& K, TcView& V, const ObsLoad& cur,
-                                               double (&gu)[9], double& cost, float4 (&ur)[4], float4 (&vr)[4],
-                                               double* __restrict__ res_out) {
-  // ================= FP64: forward, residual, cost, gradient by reverse mode =================
-  {
-    const double X = (double)cur.X, Y = (double)cur.Y, Z = (double)cur.Z;
-    const double pt0 = fma(V.R[0], X, fma(V.R[1], Y, fma(V.R[2], Z, V.t[0])));
-    const double pt1 = fma(V.R[3], X, fma(V.R[4], Y, fma(V.R[5], Z, V.t[1])));
-    const double pt2 = fma(V.R[6], X, fma(V.R[7], Y, fma(V.R[8], Z, V.t[2])));
-    const double iz = fast_rcp(pt2);
-    const double xn = pt0 * iz, yn = pt1 * iz;
-    const double xx = xn * xn, yy = yn * yn, xy = xn * yn;
-    const double r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
-    // m = 1 + k1 r2 + k2 r4 + k3 r6 and mp = dm/dr2 by Horner (no derived constants to keep in registers)
-    const double h2 = fma(r2, K.k3, K.k2), h1 = fma(r2, h2, K.k1);
-    const double m = fma(r2, h1, 1.0), mp = fma(r2, fma(r2, K.k3, h2), h1);
-    const double a1 = xy + xy, a2 = fma(2.0, xx, r2), a3 = fma(2.0, yy, r2);
-    const double xd = fma(xn, m, fma(K.p1, a1, K.p2 * a2));
-    const double yd = fma(yn, m, fma(K.p2, a1, K.p1 * a3));
-    double ru = fma(K.fx, xd, K.cx - (double)cur.mu);
-    double rv = fma(K.fy, yd, K.cy - (double)cur.mv);
-    ru = cur.valid ? ru : 0.0;
-    rv = cur.valid ? rv : 0.0;
-    if (RES) {
-      if (cur.valid) {
-        res_out[2 * (cur.o - d.obs_base)] = ru;
-        res_out[2 * (cur.o - d.obs_base) + 1] = rv;
-      }
+__device__ __forceinline__ void tc_fp64_observation(const IntrDev& d, const TcConst64& K, const double (&R)[9],
+                                                    const double (&t)[3], const ObsIn& cur, double (&gu)[9],
+                                                    double (&gv)[6], double& cost, double* __restrict__ res_out) {
+  const double X = (double)cur.X, Y = (double)cur.Y, Z = (double)cur.Z;
+  const double dmu = (double)cur.mu, dmv = (double)cur.mv;
+  const double pt0 = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, t[0])));
+  const double pt1 = fma(R[3], X, fma(R[4], Y, fma(R[5], Z, t[1])));
+  const double pt2 = fma(R[6], X, fma(R[7], Y, fma(R[8], Z, t[2])));
+  const double iz = fast_rcp(pt2);
+  const double xn = pt0 * iz, yn = pt1 * iz;
+  const double xx = xn * xn, yy = yn * yn, xy = xn * yn;
+  const double r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
+  // m = 1 + k1 r2 + k2 r4 + k3 r6 and mp = dm/dr2 by Horner (no derived constants to keep in registers)
+  const double h2 = fma(r2, K.k3, K.k2), h1 = fma(r2, h2, K.k1);
+  const double m = fma(r2, h1, 1.0), mp = fma(r2, fma(r2, K.k3, h2), h1);
+  const double a1 = xy + xy, a2 = fma(2.0, xx, r2), a3 = fma(2.0, yy, r2);
+  const double xd = fma(xn, m, fma(K.p1, a1, K.p2 * a2));
+  const double yd = fma(yn, m, fma(K.p2, a1, K.p1 * a3));
+  double ru = fma(K.fx, xd, K.cx - dmu);
+  double rv = fma(K.fy, yd, K.cy - dmv);
+  ru = cur.valid ? ru : 0.0;
+  rv = cur.valid ? rv : 0.0;
+  if (RES) {
+    if (cur.valid) {
+      res_out[2 * (cur.o - d.obs_base)] = ru;
+      res_out[2 * (cur.o - d.obs_base) + 1] = rv;
     }
-    cost = fma(ru, ru, fma(rv, rv, cost));
-    const double tu = K.fx * ru, tv = K.fy * rv;  // d cost / d(xd, yd)
-    gu[0] = fma(xd, ru, gu[0]);
-    gu[1] = fma(yd, rv, gu[1]);
-    gu[2] += ru;
-    gu[3] += rv;
-    const double sr = fma(xn, tu, yn * tv);
-    gu[4] = fma(r2, sr, gu[4]);
-    gu[5] = fma(r4, sr, gu[5]);
-    gu[8] = fma(r6, sr, gu[8]);
-    gu[6] = fma(a1, tu, fma(a3, tv, gu[6]));
-    gu[7] = fma(a2, tu, fma(a1, tv, gu[7]));
-    // d(xd,yd)/d(xn,yn): F00 = m + 2xx mp + 2p1 yn + 6p2 xn, F01 = a1 mp + 2p1 xn + 2p2 yn,
-    // F11 = m + 2yy mp + 2p2 xn + 6p1 yn
-    const double tx = xn + xn, ty = yn + yn;
-    const double u1 = K.p1 * ty, u2 = K.p2 * tx, base = m + (u1 + u2);
-    const double F00 = fma(2.0, u2, fma(a2 - r2, mp, base));
-    const double F01 = fma(a1, mp, fma(K.p1, tx, K.p2 * ty));
-    const double F11 = fma(2.0, u1, fma(a3 - r2, mp, base));
-    const double w0 = fma(F00, tu, F01 * tv) * iz, w1 = fma(F01, tu, F11 * tv) * iz;  // d cost / d(pt0, pt1)
-    const double w2 = -fma(xn, w0, yn * w1);                                          // d cost / d pt2
-    V.gv[3] += w0;
-    V.gv[4] += w1;
-    V.gv[5] += w2;
-    // rotation tangent: 2 (y x w) with y = pt - t; accumulated as pt x w, fixed up per view
-    V.gv[0] = fma(pt1, w2, fma(-pt2, w1, V.gv[0]));
-    V.gv[1] = fma(pt2, w0, fma(-pt0, w2, V.gv[1]));
-    V.gv[2] = fma(pt0, w1, fma(-pt1, w0, V.gv[2]));
   }
-  // ================= FP32: the two Jacobian rows =================
-  {
-    const float one = cur.valid ? 1.0f : 0.0f;
-    const float fxv = cur.valid ? K.fxf : 0.0f, fyv = cur.valid ? K.fyf : 0.0f;
-    const float X = cur.X, Y = cur.Y, Z = cur.Z;
-    const float y0 = fmaf(V.Rf[0], X, fmaf(V.Rf[1], Y, V.Rf[2] * Z));
-    const float y1 = fmaf(V.Rf[3], X, fmaf(V.Rf[4], Y, V.Rf[5] * Z));
-    const float y2 = fmaf(V.Rf[6], X, fmaf(V.Rf[7], Y, V.Rf[8] * Z));
-    const float iz = fast_rcpf(y2 + V.tf[2]);
-    const float xn = (y0 + V.tf[0]) * iz, yn = (y1 + V.tf[1]) * iz;
-    const float xx = xn * xn, yy = yn * yn, xy = xn * yn;
-    const float r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
-    const float h2 = fmaf(r2, K.k3f, K.k2f), h1 = fmaf(r2, h2, K.k1f);
-    const float m = fmaf(r2, h1, 1.0f), mp = fmaf(r2, fmaf(r2, K.k3f, h2), h1);
-    const float a1 = xy + xy, a2 = fmaf(2.0f, xx, r2), a3 = fmaf(2.0f, yy, r2);
-    const float xd = fmaf(xn, m, fmaf(K.p1f, a1, K.p2f * a2));
-    const float yd = fmaf(yn, m, fmaf(K.p2f, a1, K.p1f * a3));
-    const float tx = xn + xn, ty = yn + yn;
-    const float u1 = K.p1f * ty, u2 = K.p2f * tx, base = m + (u1 + u2);
-    const float F00 = fmaf(2.0f, u2, fmaf(a2 - r2, mp, base));
-    const float F01 = fmaf(a1, mp, fmaf(K.p1f, tx, K.p2f * ty));
-    const float F11 = fmaf(2.0f, u1, fmaf(a3 - r2, mp, base));
-    const float fiz = fxv * iz, giz = fyv * iz;
-    // d(u,v)/d(camera point): rows (A0 A1 A2), (B0 B1 B2)
-    const float A0 = fiz * F00, A1 = fiz * F01, B0 = giz * F01, B1 = giz * F11;
-    const float A2 = -fmaf(A0, xn, A1 * yn), B2 = -fmaf(B0, xn, B1 * yn);
-    // d(camera point)/d(rotation tangent) = 2 (y x .)
-    const float z0 = y0 + y0, z1 = y1 + y1, z2 = y2 + y2;
-    const float ju0 = fmaf(z1, A2, -z2 * A1), ju1 = fmaf(z2, A0, -z0 * A2), ju2 = fmaf(z0, A1, -z1 * A0);
-    const float jv0 = fmaf(z1, B2, -z2 * B1), jv1 = fmaf(z2, B0, -z0 * B2), jv2 = fmaf(z0, B1, -z1 * B0);
-    const float fxn = fxv * xn, fyn = fyv * yn;
-    // tile order of a row: product column m sits at position (m % 8) * 2 + m / 8, so one
-    // LDS.64 at float 2g returns columns g and g + 8:
-    //   [c0 c8 | c1 c9 | c2 c10 | c3 c11 | c4 c12 | c5 c13 | c6 c14 | c7 c15]
-    // u row: c0..5 pose, c6 = xd (fx), c7 = 0 (fy), c8 = 1 (px), c9 = 0 (py), c10..14 = k1 k2 p1 p2 k3
-    ur[0] = make_float4(ju0, one, ju1, 0.0f);
-    ur[1] = make_float4(ju2, fxn * r2, A0, fxn * r4);
-    ur[2] = make_float4(A1, fxv * a1, A2, fxv * a2);
-    ur[3] = make_float4(xd * one, fxn * r6, 0.0f, 0.0f);
-    // v row: c6 = 0, c7 = yd (fy), c8 = 0, c9 = 1 (py)
-    vr[0] = make_float4(jv0, 0.0f, jv1, one);
-    vr[1] = make_float4(jv2, fyn * r2, B0, fyn * r4);
-    vr[2] = make_float4(B1, fyv * a3, B2, fyv * a1);
-    vr[3] = make_float4(0.0f, fyn * r6, yd * one, 0.0f);
-  }
+  cost = fma(ru, ru, fma(rv, rv, cost));
+  const double tu = K.fx * ru, tv = K.fy * rv;  // d cost / d(xd, yd)
+  gu[0] = fma(xd, ru, gu[0]);
+  gu[1] = fma(yd, rv, gu[1]);
+  gu[2] += ru;
+  gu[3] += rv;
+  const double sr = fma(xn, tu, yn * tv);
+  gu[4] = fma(r2, sr, gu[4]);
+  gu[5] = fma(r4, sr, gu[5]);
+  gu[8] = fma(r6, sr, gu[8]);
+  gu[6] = fma(a1, tu, fma(a3, tv, gu[6]));
+  gu[7] = fma(a2, tu, fma(a1, tv, gu[7]));
+  // d(xd,yd)/d(xn,yn): F00 = m + 2xx mp + 2p1 yn + 6p2 xn, F01 = a1 mp + 2p1 xn + 2p2 yn,
+  // F11 = m + 2yy mp + 2p2 xn + 6p1 yn
+  const double tx = xn + xn, ty = yn + yn;
+  const double u1 = K.p1 * ty, u2 = K.p2 * tx, base = m + (u1 + u2);
+  const double F00 = fma(2.0, u2, fma(a2 - r2, mp, base));
+  const double F01 = fma(a1, mp, fma(K.p1, tx, K.p2 * ty));
+  const double F11 = fma(2.0, u1, fma(a3 - r2, mp, base));
+  const double w0 = fma(F00, tu, F01 * tv) * iz, w1 = fma(F01, tu, F11 * tv) * iz;  // d cost / d(pt0, pt1)
+  const double w2 = -fma(xn, w0, yn * w1);                                          // d cost / d pt2
+  gv[3] += w0;
+  gv[4] += w1;
+  gv[5] += w2;
+  // rotation tangent: 2 (y x w) with y = pt - t; accumulated as pt x w, fixed up per view
+  gv[0] = fma(pt1, w2, fma(-pt2, w1, gv[0]));
+  gv[1] = fma(pt2, w0, fma(-pt0, w2, gv[1]));
+  gv[2] = fma(pt0, w1, fma(-pt1, w0, gv[2]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobian role: the two float32 Jacobian rows of one observation per lane, in tile order.
+// Invalid lanes produce all-zero rows.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fp32_rows(const TcConst32& K, const float (&Rf)[9], const float (&tf)[3],
+                                             float X, float Y, float Z, bool valid, float4 (&ur)[4],
+                                             float4 (&vr)[4]) {
+  const float one = valid ? 1.0f : 0.0f;
+  const float fxv = valid ? K.fx : 0.0f, fyv = valid ? K.fy : 0.0f;
+  const float y0 = fmaf(Rf[0], X, fmaf(Rf[1], Y, Rf[2] * Z));
+  const float y1 = fmaf(Rf[3], X, fmaf(Rf[4], Y, Rf[5] * Z));
+  const float y2 = fmaf(Rf[6], X, fmaf(Rf[7], Y, Rf[8] * Z));
+  const float iz = fast_rcpf(y2 + tf[2]);
+  const float xn = (y0 + tf[0]) * iz, yn = (y1 + tf[1]) * iz;
+  const float xx = xn * xn, yy = yn * yn, xy = xn * yn;
+  const float r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
+  const float h2 = fmaf(r2, K.k3, K.k2), h1 = fmaf(r2, h2, K.k1);
+  const float m = fmaf(r2, h1, 1.0f), mp = fmaf(r2, fmaf(r2, K.k3, h2), h1);
+  const float a1 = xy + xy, a2 = fmaf(2.0f, xx, r2), a3 = fmaf(2.0f, yy, r2);
+  const float xd = fmaf(xn, m, fmaf(K.p1, a1, K.p2 * a2));
+  const float yd = fmaf(yn, m, fmaf(K.p2, a1, K.p1 * a3));
+  const float tx = xn + xn, ty = yn + yn;
+  const float u1 = K.p1 * ty, u2 = K.p2 * tx, base = m + (u1 + u2);
+  const float F00 = fmaf(2.0f, u2, fmaf(a2 - r2, mp, base));
+  const float F01 = fmaf(a1, mp, fmaf(K.p1, tx, K.p2 * ty));
+  const float F11 = fmaf(2.0f, u1, fmaf(a3 - r2, mp, base));
+  const float fiz = fxv * iz, giz = fyv * iz;
+  // d(u,v)/d(camera point): rows (A0 A1 A2), (B0 B1 B2)
+  const float A0 = fiz * F00, A1 = fiz * F01, B0 = giz * F01, B1 = giz * F11;
+  const float A2 = -fmaf(A0, xn, A1 * yn), B2 = -fmaf(B0, xn, B1 * yn);
+  // d(camera point)/d(rotation tangent) = 2 (y x .)
+  const float z0 = y0 + y0, z1 = y1 + y1, z2 = y2 + y2;
+  const float ju0 = fmaf(z1, A2, -z2 * A1), ju1 = fmaf(z2, A0, -z0 * A2), ju2 = fmaf(z0, A1, -z1 * A0);
+  const float jv0 = fmaf(z1, B2, -z2 * B1), jv1 = fmaf(z2, B0, -z0 * B2), jv2 = fmaf(z0, B1, -z1 * B0);
+  const float fxn = fxv * xn, fyn = fyv * yn;
+  // tile order of a row: product column m sits at position (m % 8) * 2 + m / 8, so one
+  // LDS.64 at float 2g returns columns g and g + 8:
+  //   [c0 c8 | c1 c9 | c2 c10 | c3 c11 | c4 c12 | c5 c13 | c6 c14 | c7 c15]
+  // u row: c0..5 pose, c6 = xd (fx), c7 = 0 (fy), c8 = 1 (px), c9 = 0 (py), c10..14 = k1 k2 p1 p2 k3
+  ur[0] = make_float4(ju0, one, ju1, 0.0f);
+  ur[1] = make_float4(ju2, fxn * r2, A0, fxn * r4);
+  ur[2] = make_float4(A1, fxv * a1, A2, fxv * a2);
+  ur[3] = make_float4(xd * one, fxn * r6, 0.0f, 0.0f);
+  // v row: c6 = 0, c7 = yd (fy), c8 = 0, c9 = 1 (py)
+  vr[0] = make_float4(jv0, 0.0f, jv1, one);
+  vr[1] = make_float4(jv2, fyn * r2, B0, fyn * r4);
+  vr[2] = make_float4(B1, fyv * a3, B2, fyv * a1);
+  vr[3] = make_float4(0.0f, fyn * r6, yd * one, 0.0f);
 }
 
 // rows 0..31 of a tile = u rows of the 32 observations, rows 32..63 = their v rows
@@ -233,37 +248,132 @@ __device__ __forceinline__ void tc_contract(const float* tile, int g, int tig, i
 // Asynchronous prefetch of one 32-observation chunk into the warp's staging ring (LDGSTS: no
 // registers are held while the loads are in flight, so ptxas cannot sink them next to their use -
 // it did exactly that with plain prefetch loads).  Lanes past the end of the view zero-fill.
+// NARR = 5: u v X Y Z (FP64 role), NARR = 3: X Y Z (Jacobian role; the other role's copy of the
+// same lines is an L1/L2 hit, HBM traffic stays 20 B per observation).  One commit group per
+// chunk, so "wait_group kTcStages - 1" means "the chunk I am about to consume has landed".
+template <int NARR>
 __device__ __forceinline__ void tc_prefetch(float* stage, const IntrDev& d, int64_t idx, int64_t end, int lane) {
   const bool valid = idx < end;
   const int64_t o = valid ? idx : 0;
   const int sz = valid ? 4 : 0;
   const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + lane);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(d.u + o), "r"(sz) : "memory");
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128), "l"(d.v + o), "r"(sz) : "memory");
+  if (NARR == 5) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(d.u + o), "r"(sz) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128), "l"(d.v + o), "r"(sz) : "memory");
+  }
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 256), "l"(d.X + o), "r"(sz) : "memory");
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 384), "l"(d.Y + o), "r"(sz) : "memory");
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 512), "l"(d.Z + o), "r"(sz) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// wait until at most kTcStages - 1 younger groups are pending, then read this lane's observation
-__device__ __forceinline__ void tc_take(ObsLoad& L, const float* stage, int64_t idx, int64_t end, int lane) {
+template <int NARR>
+__device__ __forceinline__ void tc_take(ObsIn& L, const float* stage, int64_t idx, int64_t end, int lane) {
   asm volatile("cp.async.wait_group %0;" ::"n"(kTcStages - 1) : "memory");
   L.valid = idx < end;
   L.o = idx;
-  L.mu = stage[lane];
-  L.mv = stage[32 + lane];
+  if (NARR == 5) {
+    L.mu = stage[lane];
+    L.mv = stage[32 + lane];
+  }
   L.X = stage[64 + lane];
   L.Y = stage[96 + lane];
   L.Z = stage[128 + lane];
 }
 
-template <bool RES, int kTcWarps>
+// ---------------------------------------------------------------------------------------------
+// Candidate poses, one thread per view: pose (+) delta_v with delta_v = -z - Y du (the
+// back-substitution of the reduced solve), written as the candidate pose and as the rotation
+// matrix + translation the sweep consumes; per-CTA partial sums of the model terms g'd and d'Dd.
+// Grid: schur_split CTAs per work item (the elimination kernel's split).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStepThreads = 128;
+__global__ void __launch_bounds__(kStepThreads) k_intr_step(IntrDev d) {
+  __shared__ double s_du[9];
+  __shared__ double s_red[2][kStepThreads / 32];
+  __shared__ int s_meta[2];
+  WorkItem it = d.items[blockIdx.x / d.schur_split];
+  {
+    const int sub = blockIdx.x % d.schur_split, nv = it.v1 - it.v0;
+    const int a = it.v0 + (int)((int64_t)nv * sub / d.schur_split);
+    const int b = it.v0 + (int)((int64_t)nv * (sub + 1) / d.schur_split);
+    it.v0 = a;
+    it.v1 = b;
+  }
+  IntrState& ps = d.ps[it.problem];
+  if (threadIdx.x == 0) {
+    s_meta[0] = ps.lm.par;
+    s_meta[1] = (ps.lm.status == 0 && ps.lm.solve_ok) ? 1 : 0;
+  }
+  if (threadIdx.x < 9) s_du[threadIdx.x] = ps.du[threadIdx.x];
+  __syncthreads();
+  if (!s_meta[1]) return;
+  const int par = s_meta[0];
+  double gTd = 0.0, dDd = 0.0;
+  for (int64_t v = it.v0 + threadIdx.x; v < it.v1; v += kStepThreads) {
+    const double* yz = d.yz + (size_t)v * kYz;
+    double dl[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double s = -yz[54 + a];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) s -= yz[a * 9 + j] * s_du[j];
+      dl[a] = s;
+      gTd += yz[60 + a] * s;
+      dDd += s * s * yz[66 + a];
+    }
+    const double* pc = d.pose[par] + (size_t)v * kPose;
+    const double q[4] = {pc[0], pc[1], pc[2], pc[3]};
+    double qn[4], R[9];
+    quat_plus(q, dl[0], dl[1], dl[2], qn);
+    const double t0 = pc[4] + dl[3], t1 = pc[5] + dl[4], t2 = pc[6] + dl[5];
+    double* pn = d.pose[par ^ 1] + (size_t)v * kPose;
+    pn[0] = qn[0]; pn[1] = qn[1]; pn[2] = qn[2]; pn[3] = qn[3];
+    pn[4] = t0; pn[5] = t1; pn[6] = t2;
+    quat_to_rot(qn, R);
+    double2* rt = reinterpret_cast<double2*>(d.rt + (size_t)v * 12);
+    rt[0] = make_double2(R[0], R[1]);
+    rt[1] = make_double2(R[2], R[3]);
+    rt[2] = make_double2(R[4], R[5]);
+    rt[3] = make_double2(R[6], R[7]);
+    rt[4] = make_double2(R[8], t0);
+    rt[5] = make_double2(t1, t2);
+  }
+  // fixed-order block reduction (bit-reproducible)
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    gTd += __shfl_xor_sync(0xffffffffu, gTd, s);
+    dDd += __shfl_xor_sync(0xffffffffu, dDd, s);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_red[0][threadIdx.x >> 5] = gTd;
+    s_red[1][threadIdx.x >> 5] = dDd;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kStepThreads / 32; ++w) s += s_red[threadIdx.x][w];
+    d.step_part[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The sweep.  One CTA per work item; the first kTcD warps run the FP64 role, the others the
+// Jacobian role, so the FP64 pipe and the FP32 + tensor pipes of every SM sub-partition are fed
+// by different warps at the same time.  Each role walks ALL views of the item on its own
+// (view v goes to role-warp v mod role size: static, so sums are bit-reproducible); the roles
+// share nothing, so there is no synchronisation inside the loops, and the second reader of an
+// observation line hits L1/L2 (HBM traffic stays 20 B per observation).  The split 7 : 9 balances
+// the measured role times (FP64 role 0.78 of the Jacobian role per observation).
+// ---------------------------------------------------------------------------------------------
+template <bool RES>
 __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, double* __restrict__ res_out) {
-  extern __shared__ __align__(16) unsigned char s_dyn[];  // kTcSmem bytes: partials, then the tiles
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   double(*s_part)[kSweepPart] = reinterpret_cast<double(*)[kSweepPart]>(s_dyn);
-  float* s_tiles = reinterpret_cast<float*>(s_dyn + sizeof(double) * kTcWarps * kSweepPart);
-  __shared__ double s_k[9], s_du[9];
+  float* s_rings = reinterpret_cast<float*>(s_dyn + sizeof(double) * kTcWarps * kSweepPart);
+  float* s_tiles = s_rings + kTcWarps * kTcRing;
+  __shared__ double s_k[9];
   __shared__ int s_meta[2];
   const WorkItem it = d.items[blockIdx.x];
   IntrState& ps = d.ps[it.problem];
@@ -274,124 +384,49 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
   __syncthreads();
   if (!s_meta[1]) return;
   const int par = s_meta[0];
-  if (threadIdx.x < 9) {
-    s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
-    s_du[threadIdx.x] = ps.du[threadIdx.x];
-  }
+  if (threadIdx.x < 9) s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
   for (int i = threadIdx.x; i < kTcWarps * kSweepPart; i += blockDim.x) (&s_part[0][0])[i] = 0.0;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, tig = lane & 3;
-  float* tiles = s_tiles + warp * (2 * kTcTile + kTcStages * kTcStage);
-  float* stages = tiles + 2 * kTcTile;
+  const bool jac_role = warp >= kTcD;
+  float* ring = s_rings + warp * kTcRing;
   double* upart = s_part[warp];
 
-  TcConst K;
-  K.fx = s_k[0]; K.fy = s_k[1]; K.cx = s_k[2]; K.cy = s_k[3];
-  K.k1 = s_k[4]; K.k2 = s_k[5]; K.p1 = s_k[6]; K.p2 = s_k[7]; K.k3 = s_k[8];
-  K.fxf = (float)K.fx; K.fyf = (float)K.fy;
-  K.k1f = (float)K.k1; K.k2f = (float)K.k2; K.p1f = (float)K.p1; K.p2f = (float)K.p2; K.k3f = (float)K.k3;
-  // opaque: keeps ptxas from re-converting the constants per observation (F2F runs at 1/8 rate)
-  asm volatile("" : "+f"(K.fxf), "+f"(K.fyf), "+f"(K.k1f), "+f"(K.k2f), "+f"(K.p1f), "+f"(K.p2f), "+f"(K.k3f));
-
-  double gu[9], cost = 0.0, gTd = 0.0, dDd = 0.0;
+  if (!jac_role) {
+    // =========================== FP64 role ===========================
+    TcConst64 K;
+    K.fx = s_k[0]; K.fy = s_k[1]; K.cx = s_k[2]; K.cy = s_k[3];
+    K.k1 = s_k[4]; K.k2 = s_k[5]; K.p1 = s_k[6]; K.p2 = s_k[7]; K.k3 = s_k[8];
+    double gu[9], cost = 0.0;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) gu[i] = 0.0;
-
-  for (int64_t v = it.v0 + warp; v < it.v1; v += kTcWarps) {
-    // the first chunks of the view stream in while the candidate pose is being formed
-    const int64_t o0 = d.view_off[v], o1 = d.view_off[v + 1];
-    tc_prefetch(stages, d, o0 + lane, o1, lane);
-    tc_prefetch(stages + kTcStage, d, o0 + 32 + lane, o1, lane);
-    // ---------------- candidate pose of the view: current (+) (-z - Y du)
-    TcView V;
-    {
-      double dl = 0.0;
-      const double* yz = d.yz + (size_t)v * kYz;
-      if (lane < 6) {
-        dl = -yz[54 + lane];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) dl -= yz[lane * 9 + j] * s_du[j];
-        gTd += yz[60 + lane] * dl;
-        dDd += dl * dl * yz[66 + lane];
+    for (int i = 0; i < 9; ++i) gu[i] = 0.0;
+    for (int v = it.v0 + warp; v < it.v1; v += kTcD) {
+      const int64_t o0 = d.view_off[v], o1 = d.view_off[v + 1];
+      tc_prefetch<5>(ring, d, o0 + lane, o1, lane);
+      tc_prefetch<5>(ring + kTcStage, d, o0 + 32 + lane, o1, lane);
+      double R[9], t[3], gv[6];
+      {
+        const double2* rt = reinterpret_cast<const double2*>(d.rt + (size_t)v * 12);
+        const double2 a = rt[0], b = rt[1], c = rt[2], e = rt[3], f = rt[4], h = rt[5];
+        R[0] = a.x; R[1] = a.y; R[2] = b.x; R[3] = b.y; R[4] = c.x; R[5] = c.y;
+        R[6] = e.x; R[7] = e.y; R[8] = f.x; t[0] = f.y; t[1] = h.x; t[2] = h.y;
       }
-      const double d0 = __shfl_sync(0xffffffffu, dl, 0), d1 = __shfl_sync(0xffffffffu, dl, 1),
-                   d2 = __shfl_sync(0xffffffffu, dl, 2), d3 = __shfl_sync(0xffffffffu, dl, 3),
-                   d4 = __shfl_sync(0xffffffffu, dl, 4), d5 = __shfl_sync(0xffffffffu, dl, 5);
-      const double* pc = d.pose[par] + (size_t)v * kPose;
-      double q[4] = {pc[0], pc[1], pc[2], pc[3]};
-      double qn[4];
-      quat_plus(q, d0, d1, d2, qn);
-      V.t[0] = pc[4] + d3;
-      V.t[1] = pc[5] + d4;
-      V.t[2] = pc[6] + d5;
-      if (lane < 7) {
-        double* pn = d.pose[par ^ 1] + (size_t)v * kPose;
-        const double val = lane == 0 ? qn[0] : lane == 1 ? qn[1] : lane == 2 ? qn[2] : lane == 3 ? qn[3]
-                         : lane == 4 ? V.t[0] : lane == 5 ? V.t[1] : V.t[2];
-        pn[lane] = val;
-      }
-      quat_to_rot(qn, V.R);
-    }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      V.Rf[i] = (float)V.R[i];
-      asm volatile("" : "+f"(V.Rf[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      V.tf[i] = (float)V.t[i];
-      asm volatile("" : "+f"(V.tf[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) V.gv[i] = 0.0;
-    // product columns 0..7 (c0*) and 8..15 (c1*), two accumulator sets each
-    float c0a[4] = {0.f, 0.f, 0.f, 0.f}, c0b[4] = {0.f, 0.f, 0.f, 0.f};
-    float c1a[4] = {0.f, 0.f, 0.f, 0.f}, c1b[4] = {0.f, 0.f, 0.f, 0.f};
-
-    if (o1 > o0) {
-      // software pipeline over 32-observation chunks: while chunk j's rows are being computed
-      // (FP64 + FP32 pipes), chunk j-1's tile is contracted (LDS + tensor pipe) and chunk j+2 is
-      // in flight from HBM; the streams are independent inside one loop body
-      ObsLoad cur;
-      float4 ur[4], vr[4];
-      tc_prefetch(stages + 2 * kTcStage, d, o0 + 64 + lane, o1, lane);
-      tc_take(cur, stages, o0 + lane, o1, lane);
-      tc_observation<RES>(d, K, V, cur, gu, cost, ur, vr, res_out);
-      tc_store_rows(tiles, lane, ur, vr);
-      __syncwarp();
-      int buf = 0, st = 1;  // tile that holds chunk j-1, stage that holds chunk j
-      int64_t ob = o0 + 32;
-      for (; ob < o1; ob += 32) {
-        const int st_free = st == 0 ? kTcStages - 1 : st - 1;  // chunk j-1's stage: consumed
-        tc_prefetch(stages + st_free * kTcStage, d, ob + 64 + lane, o1, lane);
-        tc_take(cur, stages + st * kTcStage, ob + lane, o1, lane);
-        tc_contract<true>(tiles + buf * kTcTile, g, tig, 32, c0a, c0b, c1a, c1b);
-        tc_observation<RES>(d, K, V, cur, gu, cost, ur, vr, res_out);
-        buf ^= 1;
+      for (int i = 0; i < 6; ++i) gv[i] = 0.0;
+      int st = 0;
+      for (int64_t ob = o0; ob < o1; ob += 32) {
+        const int st_free = st == 0 ? kTcStages - 1 : st - 1;  // the previous chunk's stage: consumed
+        tc_prefetch<5>(ring + st_free * kTcStage, d, ob + 64 + lane, o1, lane);
+        ObsIn cur;
+        tc_take<5>(cur, ring + st * kTcStage, ob + lane, o1, lane);
+        tc_fp64_observation<RES>(d, K, R, t, cur, gu, gv, cost, res_out);
         st = st == kTcStages - 1 ? 0 : st + 1;
-        tc_store_rows(tiles + buf * kTcTile, lane, ur, vr);
-        __syncwarp();
       }
-      tc_contract<false>(tiles + buf * kTcTile, g, tig, (int)(o1 - (ob - 32)), c0a, c0b, c1a, c1b);
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    // ---------------- per-view epilogue: blocks, gradient, U contribution
-    double* blk = d.blk[par ^ 1] + (size_t)v * kBlk;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int nt = i >> 2, e = i & 3;
-      const int row = g + ((e & 2) ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
-      const float val = nt == 0 ? c0a[e] + c0b[e] : c1a[e] + c1b[e];
-      const int bs = tc_blk_slot(row, col), us = tc_u_slot(row, col);
-      if (bs >= 0) blk[bs] = (double)val;
-      if (us >= 0) upart[us] += (double)val;  // one owner lane per slot within the warp
-    }
-    {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      // per-view gradient: reduce over lanes, fix up the rotation part, store
       double tmp[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) tmp[i] = i < 6 ? V.gv[i] : 0.0;
+      for (int i = 0; i < 8; ++i) tmp[i] = i < 6 ? gv[i] : 0.0;
       double r = group_reduce<8, double>(tmp, lane & 7);
       r += __shfl_xor_sync(0xffffffffu, r, 8);
       r += __shfl_xor_sync(0xffffffffu, r, 16);
@@ -399,35 +434,95 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
       const double sw0 = __shfl_sync(0xffffffffu, r, 3), sw1 = __shfl_sync(0xffffffffu, r, 4),
                    sw2 = __shfl_sync(0xffffffffu, r, 5);
       double out = r;
-      if (lane == 0) out = 2.0 * (r - (V.t[1] * sw2 - V.t[2] * sw1));
-      if (lane == 1) out = 2.0 * (r - (V.t[2] * sw0 - V.t[0] * sw2));
-      if (lane == 2) out = 2.0 * (r - (V.t[0] * sw1 - V.t[1] * sw0));
-      if (lane < 6) blk[21 + lane] = out;
+      if (lane == 0) out = 2.0 * (r - (t[1] * sw2 - t[2] * sw1));
+      if (lane == 1) out = 2.0 * (r - (t[2] * sw0 - t[0] * sw2));
+      if (lane == 2) out = 2.0 * (r - (t[0] * sw1 - t[1] * sw0));
+      if (lane < 6) d.blk[par ^ 1][(size_t)v * kBlk + 21 + lane] = out;
     }
-  }
-  // ---------------- end of item: lane-private sums -> warp partial -> one partial per CTA
-  {
-    // partial layout: [0] sum r^2 | [7] g'd | [8] d'Dd | [16..24] g_u (U slots were filled per view)
+    // lane-private sums -> the team's partial: [0] sum r^2 | [16..24] g_u
     double tmp[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) tmp[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < 9; ++i) tmp[i] = gu[i];
     tmp[9] = cost;
-    tmp[10] = gTd;
-    tmp[11] = dDd;
     double r = group_reduce<16, double>(tmp, lane & 15);
     r += __shfl_xor_sync(0xffffffffu, r, 16);
     if (lane < 9) upart[16 + lane] = r;
     else if (lane == 9) upart[0] = r;
-    else if (lane == 10) upart[7] = r;
-    else if (lane == 11) upart[8] = r;
+  } else {
+    // =========================== Jacobian + tensor role ===========================
+    const int g = lane >> 2, tig = lane & 3;
+    float* tiles = s_tiles + (warp - kTcD) * 2 * kTcTile;
+    TcConst32 K;
+    K.fx = (float)s_k[0]; K.fy = (float)s_k[1];
+    K.k1 = (float)s_k[4]; K.k2 = (float)s_k[5]; K.p1 = (float)s_k[6]; K.p2 = (float)s_k[7]; K.k3 = (float)s_k[8];
+    for (int v = it.v0 + (warp - kTcD); v < it.v1; v += kTcJ) {
+      const int64_t o0 = d.view_off[v], o1 = d.view_off[v + 1];
+      tc_prefetch<3>(ring, d, o0 + lane, o1, lane);
+      tc_prefetch<3>(ring + kTcStage, d, o0 + 32 + lane, o1, lane);
+      float Rf[9], tf[3];
+      {
+        const double2* rt = reinterpret_cast<const double2*>(d.rt + (size_t)v * 12);
+        const double2 a = rt[0], b = rt[1], c = rt[2], e = rt[3], f = rt[4], h = rt[5];
+        Rf[0] = (float)a.x; Rf[1] = (float)a.y; Rf[2] = (float)b.x; Rf[3] = (float)b.y; Rf[4] = (float)c.x;
+        Rf[5] = (float)c.y; Rf[6] = (float)e.x; Rf[7] = (float)e.y; Rf[8] = (float)f.x;
+        tf[0] = (float)f.y; tf[1] = (float)h.x; tf[2] = (float)h.y;
+      }
+      // product columns 0..7 (c0*) and 8..15 (c1*), two accumulator sets each
+      float c0a[4] = {0.f, 0.f, 0.f, 0.f}, c0b[4] = {0.f, 0.f, 0.f, 0.f};
+      float c1a[4] = {0.f, 0.f, 0.f, 0.f}, c1b[4] = {0.f, 0.f, 0.f, 0.f};
+      if (o1 > o0) {
+        // software pipeline over 32-observation chunks: while chunk j's rows are being computed,
+        // chunk j-1's tile is contracted (LDS + tensor pipe) and chunks j+1, j+2 are in flight
+        ObsIn cur;
+        float4 ur[4], vr[4];
+        tc_prefetch<3>(ring + 2 * kTcStage, d, o0 + 64 + lane, o1, lane);
+        tc_take<3>(cur, ring, o0 + lane, o1, lane);
+        tc_fp32_rows(K, Rf, tf, cur.X, cur.Y, cur.Z, cur.valid, ur, vr);
+        tc_store_rows(tiles, lane, ur, vr);
+        __syncwarp();
+        int buf = 0, st = 1;  // tile that holds chunk j-1, stage that holds chunk j
+        int64_t ob = o0 + 32;
+        for (; ob < o1; ob += 32) {
+          const int st_free = st == 0 ? kTcStages - 1 : st - 1;  // chunk j-1's stage: consumed
+          tc_prefetch<3>(ring + st_free * kTcStage, d, ob + 64 + lane, o1, lane);
+          tc_take<3>(cur, ring + st * kTcStage, ob + lane, o1, lane);
+          tc_contract<true>(tiles + buf * kTcTile, g, tig, 32, c0a, c0b, c1a, c1b);
+          tc_fp32_rows(K, Rf, tf, cur.X, cur.Y, cur.Z, cur.valid, ur, vr);
+          buf ^= 1;
+          st = st == kTcStages - 1 ? 0 : st + 1;
+          tc_store_rows(tiles + buf * kTcTile, lane, ur, vr);
+          __syncwarp();
+        }
+        tc_contract<false>(tiles + buf * kTcTile, g, tig, (int)(o1 - (ob - 32)), c0a, c0b, c1a, c1b);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      // per-view epilogue: V, W blocks and the view's contribution to U
+      double* blk = d.blk[par ^ 1] + (size_t)v * kBlk;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int nt = i >> 2, e = i & 3;
+        const int row = g + ((e & 2) ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
+        const float val = nt == 0 ? c0a[e] + c0b[e] : c1a[e] + c1b[e];
+        const int bs = tc_blk_slot(row, col), us = tc_u_slot(row, col);
+        if (bs >= 0) blk[bs] = (double)val;
+        if (us >= 0) upart[us] += (double)val;  // one owner lane per slot within the warp
+      }
+    }
   }
   __syncthreads();
   if (threadIdx.x < kSweepPart) {
+    // the model terms g'd, d'Dd of this item come from the candidate-pose kernel
     double s = 0.0;
+    if (threadIdx.x == 7 || threadIdx.x == 8) {
+      const int c = threadIdx.x - 7;
+      for (int i = 0; i < d.schur_split; ++i) s += d.step_part[((size_t)blockIdx.x * d.schur_split + i) * 2 + c];
+    } else {
 #pragma unroll
-    for (int w = 0; w < kTcWarps; ++w) s += s_part[w][threadIdx.x];
+      for (int w = 0; w < kTcWarps; ++w) s += s_part[w][threadIdx.x];
+    }
     d.sweep_part[(size_t)blockIdx.x * kSweepPart + threadIdx.x] = s;
   }
 }

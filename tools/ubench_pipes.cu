@@ -165,6 +165,13 @@ int main() {
   rep("mma tf32 m16n8k8 latency (1 warp/SMSP)", 8.0 * time_ms([&] { k_mma<0, 1><<<sms, 128>>>((float*)buf, 1); }), 1);
   rep("DFMA latency (1 warp/SMSP, 1 chain)", 8.0 * time_ms([&] { k_mix<1, 0, 0><<<sms, 128>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 4);
   rep("FFMA latency (1 warp/SMSP, 1 chain)", 8.0 * time_ms([&] { k_mix<0, 1, 0><<<sms, 128>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 4);
+  // does one warp saturate the FP64 pipe?  W warps per SMSP, 8 independent chains each
+  rep("DFMA x8, 1 warp/SMSP (per instr)", 8.0 * time_ms([&] { k_mix<8, 0, 0><<<sms, 128>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 32);
+  rep("DFMA x8, 2 warps/SMSP (per instr)", 4.0 * time_ms([&] { k_mix<8, 0, 0><<<sms, 256>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 32);
+  rep("DFMA x8, 4 warps/SMSP (per instr)", 2.0 * time_ms([&] { k_mix<8, 0, 0><<<sms * 2, 256>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 32);
+  rep("FFMA x16, 1 warp/SMSP (per instr)", 8.0 * time_ms([&] { k_mix<0, 16, 0><<<sms, 128>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 64);
+  rep("DFMA x8 + FFMA x16, 1 warp/SMSP (per instr of 24)", 8.0 * time_ms([&] { k_mix<8, 16, 0><<<sms, 128>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 96);
+  rep("DFMA x8 + FFMA x16, 2 warps/SMSP (per instr of 24)", 4.0 * time_ms([&] { k_mix<8, 16, 0><<<sms, 256>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 96);
   rep("DFMA x8", time_ms([&] { k_mix<8, 0, 0><<<grid, 256>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 32);
   rep("FFMA x16", time_ms([&] { k_mix<0, 16, 0><<<grid, 256>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 64);
   rep("FFMA2 x8 (per packed instr)", time_ms([&] { k_mix<0, 0, 8><<<grid, 256>>>((double*)buf, 1.0001, 0.5, 1.0001f, 0.5f); }), 32);
