@@ -560,6 +560,25 @@ __device__ inline void unpack_U(const double* r, double* U, double* gu) {
   for (int i = 0; i < 9; ++i) gu[i] = r[16 + i];
 }
 
+// accept / reject for one problem, given its reduced sweep partial r (one thread)
+__device__ inline void decide_body(IntrState& ps, const LmParams& P, bool evaluated, const double* r, int* n_done) {
+  LmState& s = ps.lm;
+  if (!evaluated) {
+    // the linear solve failed (non-PD): shrink the trust region and retry
+    lm_reject(s, P, n_done);
+    s.solve_ok = 1;
+    if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, n_done, true);
+    return;
+  }
+  const double cost_c = 0.5 * r[0];
+  const bool accept = lm_decide(s, P, cost_c, r[7] + s.gTd_u, r[8] + s.dDd_u, n_done);
+  if (accept) {
+    unpack_U(r, ps.U, ps.gu);
+    s.n_obs = r[3];
+    s.sumsq = r[0];
+  }
+}
+
 // accept / reject after a sweep.  REDUCE: sum the partials here (single GPU);
 // otherwise read the (all-reduced) red_sweep buffer.
 template <bool REDUCE>
@@ -577,39 +596,12 @@ __global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_decide(IntrDev d,
     }
   }
   if (threadIdx.x != 0) return;
-  LmState& s = ps.lm;
-  if (!evaluated) {
-    // the linear solve failed (non-PD): shrink the trust region and retry
-    lm_reject(s, P, d.n_done);
-    s.solve_ok = 1;
-    if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, d.n_done, true);
-    return;
-  }
-  const double* r = s_buf;
-  const double cost_c = 0.5 * r[0];
-  const bool accept = lm_decide(s, P, cost_c, r[7] + s.gTd_u, r[8] + s.dDd_u, d.n_done);
-  if (accept) {
-    unpack_U(r, ps.U, ps.gu);
-    s.n_obs = r[3];
-    s.sumsq = r[0];
-  }
+  decide_body(ps, P, evaluated, s_buf, d.n_done);
 }
 
-// reduced 9x9 solve.  Also evaluates the gradient norm at the current point.
-template <bool REDUCE>
-__global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, LmParams P) {
-  __shared__ double s_buf[kRedSeg * kSchurPart];
-  IntrState& ps = d.ps[blockIdx.x];
-  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
-  if (REDUCE) {
-    block_reduce_items<kSchurPart>(d.schur_part, ps.item0 * d.schur_split, ps.item1 * d.schur_split, s_buf);
-  } else {
-    if (threadIdx.x < kSchurPart) s_buf[threadIdx.x] = d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x];
-    __syncthreads();
-  }
-  if (threadIdx.x != 0) return;
+// reduced 9x9 solve for one problem, given its reduced elimination partial r (one thread)
+__device__ inline void solve_body(IntrState& ps, const LmParams& P, const double* r, int* n_done) {
   LmState& s = ps.lm;
-  const double* r = s_buf;
   const unsigned mask = ps.mask;
   const int par = s.par;
   double gDg = r[54];
@@ -622,7 +614,7 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
     return;
   }
   if (s.cost == 0.0 || sqrt(gDg) <= P.gradient_tolerance * rnorm) {
-    lm_finish(s, 1, d.n_done, false);
+    lm_finish(s, 1, n_done, false);
     return;
   }
   s.iterations++;
@@ -665,6 +657,48 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
   s.solve_ok = 1;
 }
 
+// reduced 9x9 solve.  Also evaluates the gradient norm at the current point.
+template <bool REDUCE>
+__global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, LmParams P) {
+  __shared__ double s_buf[kRedSeg * kSchurPart];
+  IntrState& ps = d.ps[blockIdx.x];
+  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
+  if (REDUCE) {
+    block_reduce_items<kSchurPart>(d.schur_part, ps.item0 * d.schur_split, ps.item1 * d.schur_split, s_buf);
+  } else {
+    if (threadIdx.x < kSchurPart) s_buf[threadIdx.x] = d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  solve_body(ps, P, s_buf, d.n_done);
+}
+
+// Batches of small problems (every problem is a single work item): one THREAD per problem
+// instead of one CTA - 4096 reduced solves are 4096 threads, not 4096 mostly idle CTAs.
+constexpr int kBatchThreads = 64;
+__global__ void __launch_bounds__(kBatchThreads) k_intr_decide_batch(IntrDev d, LmParams P, int n_problems) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_problems) return;
+  IntrState& ps = d.ps[b];
+  if (ps.lm.status != 0) return;
+  decide_body(ps, P, ps.lm.solve_ok != 0, d.sweep_part + (size_t)ps.item0 * kSweepPart, d.n_done);
+}
+
+__global__ void __launch_bounds__(kBatchThreads) k_intr_solve_batch(IntrDev d, LmParams P, int n_problems) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_problems) return;
+  IntrState& ps = d.ps[b];
+  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
+  double r[kSchurPart];
+  const double* part = d.schur_part + (size_t)ps.item0 * d.schur_split * kSchurPart;
+  for (int c = 0; c < kSchurPart; ++c) {
+    double acc = 0.0;
+    for (int i = 0; i < d.schur_split; ++i) acc += part[(size_t)i * kSchurPart + c];
+    r[c] = acc;
+  }
+  solve_body(ps, P, r, d.n_done);
+}
+
 // max |measurement| per problem (scale of the cost's rounding noise, lm_decide): one CTA per work
 // item, non-negative floats compared through their bit patterns
 __global__ void __launch_bounds__(256) k_intr_meas_scale(IntrDev d, unsigned* __restrict__ bits) {
@@ -704,6 +738,38 @@ __global__ void k_intr_init_state(IntrDev d, LmParams P, const double* intr0, co
   if (b == 0) *d.n_done = 0;
 }
 
+// results in the caller's layout: q[4V], t[3V] of the accepted pose buffer of each view's problem,
+// intr[9B] and one ccg_report per problem (so the download is four plain copies, no host loops)
+__global__ void __launch_bounds__(128) k_intr_gather(IntrDev d, const int64_t* __restrict__ problem_off, int n_problems,
+                                                    double* __restrict__ q, double* __restrict__ t,
+                                                    double* __restrict__ intr, ccg_report* __restrict__ rep) {
+  const int b = blockIdx.x;
+  const IntrState& ps = d.ps[b];
+  const int par = ps.lm.par;
+  const double* pose = d.pose[par];
+  for (int64_t v = problem_off[b] + threadIdx.x; v < problem_off[b + 1]; v += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[v * 4 + k] = pose[v * kPose + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[v * 3 + k] = pose[v * kPose + 4 + k];
+  }
+  if (threadIdx.x < 9) intr[(size_t)b * 9 + threadIdx.x] = ps.intr[par][threadIdx.x];
+  if (threadIdx.x == 0) {
+    ccg_report r;
+    r.iterations = ps.lm.iterations;
+    r.accepted = ps.lm.accepted;
+    r.rejected = ps.lm.rejected;
+    r.sweeps = ps.lm.sweeps;
+    r.termination = ps.lm.status;
+    r.pad_ = 0;
+    r.initial_cost = ps.lm.cost0;
+    r.final_cost = ps.lm.cost;
+    r.gradient_norm = ps.lm.grad_norm;
+    r.rms = ps.lm.n_obs > 0.0 ? sqrt(2.0 * ps.lm.cost / ps.lm.n_obs) : 0.0;
+    rep[b] = r;
+  }
+}
+
 }  // namespace ccg
 
 // ==========================================================================
@@ -722,13 +788,23 @@ struct ccg_intr_problem {
   std::vector<void*> allocs;
   int64_t bytes = 0;
   double *d_intr0 = nullptr, *d_pose0 = nullptr, *d_meas_scale = nullptr;
+  double *d_out_q = nullptr, *d_out_t = nullptr, *d_out_intr = nullptr;  // results in the caller's layout
+  ccg_report* d_out_rep = nullptr;
+  int64_t* d_problem_off = nullptr;
+  bool one_shot = false;             // created by ccg_intrinsics_solve*: runs once, no graph instantiation
   int2* d_item_ranges = nullptr;
   float* d_obs = nullptr;
   int group = 32;                    // lanes per view in the mixed-precision sweep (8, 16 or 32)
+  bool single_item = false;          // every problem is one work item (batch of small problems)
   std::vector<int64_t> problem_off;  // host copy
   std::vector<int64_t> problem_obs;  // observations per problem
   LmParams params;
   bool params_set = false;
+  // one LM iteration (elimination, reduced solve, candidate poses, sweep, accept/reject) as a CUDA
+  // graph: five launches become one when no per-kernel events are requested
+  cudaGraphExec_t graph_exec = nullptr;
+  LmParams graph_params;
+  int graph_kernels = 0, graph_allreduces = 0;
 };
 
 namespace {
@@ -796,6 +872,7 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
     ranges[(size_t)b].y = (int)items.size();
   }
   p->n_items = (int)items.size();
+  p->single_item = n_problems > 1 && (int64_t)items.size() == n_problems;
 
   // ---- device memory
   IntrDev& d = p->dev;
@@ -856,6 +933,8 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_item_ranges, ranges.data(), sizeof(int2) * ranges.size(), cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_pose0, pose.data(), sizeof(double) * pose.size(), cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_intr0, intr, sizeof(double) * 9 * n_problems, cudaMemcpyHostToDevice, st));
+  CCG_TRY(dev_alloc(p, &p->d_problem_off, (size_t)n_problems + 1));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_problem_off, p->problem_off.data(), sizeof(int64_t) * (n_problems + 1), cudaMemcpyHostToDevice, st));
   // max |measurement| per problem, computed on the device from the uploaded observations
   {
     unsigned* d_bits = nullptr;
@@ -937,6 +1016,9 @@ int launch_sweep_decide(ccg_intr_problem* p, const LmParams& P, Profiler& prof, 
     (*n_allreduce)++;
     k_intr_decide<false><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P);
     ctx->launches += 2;
+  } else if (p->single_item) {
+    k_intr_decide_batch<<<(nb + kBatchThreads - 1) / kBatchThreads, kBatchThreads, 0, st>>>(d, P, nb);
+    ctx->launches++;
   } else {
     k_intr_decide<true><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P);
     ctx->launches++;
@@ -961,6 +1043,9 @@ int launch_schur_solve(ccg_intr_problem* p, const LmParams& P, Profiler& prof, i
     (*n_allreduce)++;
     k_intr_solve<false><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P);
     ctx->launches += 2;
+  } else if (p->single_item) {
+    k_intr_solve_batch<<<(nb + kBatchThreads - 1) / kBatchThreads, kBatchThreads, 0, st>>>(d, P, nb);
+    ctx->launches++;
   } else {
     k_intr_solve<true><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P);
     ctx->launches++;
@@ -999,12 +1084,42 @@ int run_problem(ccg_intr_problem* p, const ccg_opts& opts, ccg_timing* timing) {
   cudaEventRecord(ctx->events[ev_total0], ctx->stream);
   CCG_TRY(reset_problem(p, P));  // restoring the initial parameters is part of the timed solve
   CCG_TRY(launch_sweep_decide(p, P, prof, nullptr, &n_allreduce));
+  // per-kernel events stay outside graphs; the NCCL allreduces of a partitioned problem are captured
+  // with the kernels (CCG_NO_GRAPH=1 disables graphs altogether)
+  static const bool no_graph = getenv("CCG_NO_GRAPH") != nullptr;
+  const bool use_graph = !prof.on && !no_graph && !p->one_shot;
+  if (use_graph && (!p->graph_exec || std::memcmp(&p->graph_params, &P, sizeof(P)) != 0)) {
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    p->graph_exec = nullptr;
+    cudaGraph_t g = nullptr;
+    const int64_t l0 = ctx->launches;
+    const int a0 = n_allreduce;
+    CCG_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    int rc = launch_schur_solve(p, P, prof, &n_allreduce);
+    if (rc == CCG_OK) rc = launch_sweep_decide(p, P, prof, nullptr, &n_allreduce);
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    p->graph_kernels = (int)(ctx->launches - l0);
+    p->graph_allreduces = n_allreduce - a0;
+    ctx->launches = l0;
+    n_allreduce = a0;
+    if (rc != CCG_OK) return rc;
+    if (e != cudaSuccess) return set_error(ctx, CCG_ERR_CUDA, "cudaStreamEndCapture", e);
+    CCG_CUDA(ctx, cudaGraphInstantiate(&p->graph_exec, g, 0));
+    cudaGraphDestroy(g);
+    p->graph_params = P;
+  }
   const int poll_every = 4;
   int done = 0;
   for (int it = 0; it <= opts.max_iterations * 2 + 64; ++it) {
-    CCG_TRY(launch_schur_solve(p, P, prof, &n_allreduce));
-    if (done >= (int)p->n_problems) break;  // that was the finalize pass
-    CCG_TRY(launch_sweep_decide(p, P, prof, nullptr, &n_allreduce));
+    if (use_graph && done < (int)p->n_problems) {
+      CCG_CUDA(ctx, cudaGraphLaunch(p->graph_exec, ctx->stream));
+      ctx->launches += p->graph_kernels;
+      n_allreduce += p->graph_allreduces;
+    } else {
+      CCG_TRY(launch_schur_solve(p, P, prof, &n_allreduce));
+      if (done >= (int)p->n_problems) break;  // that was the finalize pass
+      CCG_TRY(launch_sweep_decide(p, P, prof, nullptr, &n_allreduce));
+    }
     if ((it % poll_every) == poll_every - 1) CCG_TRY(poll_done(p, &done));
   }
   cudaEventRecord(ctx->events[ev_total1], ctx->stream);
@@ -1035,50 +1150,36 @@ int download_problem(ccg_intr_problem* p, double* intr, double* q, double* t, cc
   ccg_ctx* ctx = p->ctx;
   CCG_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t nb = p->n_problems, nv = p->n_views;
-  std::vector<IntrState> st((size_t)nb);
-  CCG_CUDA(ctx, cudaMemcpyAsync(st.data(), p->dev.ps, sizeof(IntrState) * nb, cudaMemcpyDeviceToHost, ctx->stream));
-  std::vector<double> pose0, pose1;
-  if (q || t) {
-    pose0.resize((size_t)nv * kPose);
-    pose1.resize((size_t)nv * kPose);
-    CCG_CUDA(ctx, cudaMemcpyAsync(pose0.data(), p->dev.pose[0], sizeof(double) * pose0.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    CCG_CUDA(ctx, cudaMemcpyAsync(pose1.data(), p->dev.pose[1], sizeof(double) * pose1.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  cudaStream_t st = ctx->stream;
+  if (!p->d_out_q) {
+    CCG_TRY(dev_alloc(p, &p->d_out_q, (size_t)nv * 4));
+    CCG_TRY(dev_alloc(p, &p->d_out_t, (size_t)nv * 3));
+    CCG_TRY(dev_alloc(p, &p->d_out_intr, (size_t)nb * 9));
+    CCG_TRY(dev_alloc(p, &p->d_out_rep, (size_t)nb));
   }
-  CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  k_intr_gather<<<(int)nb, 128, 0, st>>>(p->dev, p->d_problem_off, (int)nb, p->d_out_q, p->d_out_t, p->d_out_intr, p->d_out_rep);
+  ctx->launches++;
+  std::vector<ccg_report> rep_local;
+  if (!reports) {
+    rep_local.resize((size_t)nb);
+    reports = rep_local.data();
+  }
+  if (q && nv > 0) CCG_CUDA(ctx, cudaMemcpyAsync(q, p->d_out_q, sizeof(double) * nv * 4, cudaMemcpyDeviceToHost, st));
+  if (t && nv > 0) CCG_CUDA(ctx, cudaMemcpyAsync(t, p->d_out_t, sizeof(double) * nv * 3, cudaMemcpyDeviceToHost, st));
+  if (intr) CCG_CUDA(ctx, cudaMemcpyAsync(intr, p->d_out_intr, sizeof(double) * nb * 9, cudaMemcpyDeviceToHost, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(reports, p->d_out_rep, sizeof(ccg_report) * nb, cudaMemcpyDeviceToHost, st));
+  CCG_CUDA(ctx, cudaStreamSynchronize(st));
+  CCG_CUDA(ctx, cudaGetLastError());
   int rc = CCG_OK;
-  for (int64_t b = 0; b < nb; ++b) {
-    const IntrState& s = st[(size_t)b];
-    const int par = s.lm.par;
-    if (intr)
-      for (int k = 0; k < 9; ++k) intr[b * 9 + k] = s.intr[par][k];
-    if (q || t) {
-      const std::vector<double>& pose = par ? pose1 : pose0;
-      for (int64_t v = p->problem_off[(size_t)b]; v < p->problem_off[(size_t)b + 1]; ++v) {
-        if (q) for (int k = 0; k < 4; ++k) q[v * 4 + k] = pose[(size_t)v * kPose + k];
-        if (t) for (int k = 0; k < 3; ++k) t[v * 3 + k] = pose[(size_t)v * kPose + 4 + k];
-      }
-    }
-    if (reports) {
-      ccg_report& r = reports[b];
-      r.iterations = s.lm.iterations;
-      r.accepted = s.lm.accepted;
-      r.rejected = s.lm.rejected;
-      r.sweeps = s.lm.sweeps;
-      r.termination = s.lm.status;
-      r.pad_ = 0;
-      r.initial_cost = s.lm.cost0;
-      r.final_cost = s.lm.cost;
-      r.gradient_norm = s.lm.grad_norm;
-      r.rms = s.lm.n_obs > 0.0 ? std::sqrt(2.0 * s.lm.cost / s.lm.n_obs) : 0.0;
-    }
-    if (s.lm.status < 0) rc = s.lm.status;
-  }
+  for (int64_t b = 0; b < nb; ++b)
+    if (reports[b].termination < 0) rc = reports[b].termination;
   return rc;
 }
 
 void free_problem(ccg_intr_problem* p) {
   if (!p) return;
   if (p->ctx) cudaSetDevice(p->ctx->device);
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   for (void* a : p->allocs) pool_free(p->ctx, a);
   delete p;
 }
@@ -1201,6 +1302,7 @@ int ccg_intrinsics_solve_batch(ccg_ctx* ctx, const float* u, const float* v, con
   int rc = ccg_intrinsics_create(ctx, u, v, X, Y, Z, view_offsets, n_views, problem_offsets, n_problems,
                                  intr, q, t, const_intr_mask, 0, &p);
   if (rc != CCG_OK) return rc;
+  p->one_shot = true;
   rc = ccg_intrinsics_run(p, opts, nullptr);
   if (rc == CCG_OK) rc = download_problem(p, intr, q, t, reports);
   free_problem(p);
