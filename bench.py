@@ -239,6 +239,83 @@ def workload_config(name, gpus, scaling):
                      "inputs smaller than L2: L2-resident after the first sweep (roofline not meaningful)"}
 
 
+
+# ------------------------------------------------------------------ rig (C3) arm
+def run_rig(args):
+    """--workload c3: BASELINE configs[2], ExtrinsicsCalibrator::Optimize on 4 cameras x 1000 frames x
+    187 shared board points (748,000 observations, L2-resident).  Single GPU; one JSON line."""
+    import torch
+
+    import camera_calibrator_b200 as cc
+    from camera_calibrator_b200 import rig_api, synth
+
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(0)
+    ctx = cc.Context(0)
+    s = synth.rig_scene(n_cams=4, n_frames=1000, grid=(17, 11), seed=0)
+    a = (s.u, s.v, s.obs_cam, s.obs_point, s.frame_offsets, s.Xw)
+    prob = rig_api.RigProblem(ctx, *a, s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    opts = cc.default_opts(max_iterations=1000)
+    for _ in range(max(args.warmup, 3)):
+        prob.run(opts)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ctx.kernel_launches()
+    tot = 0.0
+    for _ in range(args.steps):
+        tot += prob.run(opts)["total_ms"]
+    torch.cuda.synchronize()
+    launches = ctx.kernel_launches() - l0
+    clocks = sampler.stop()
+    rep = prob.download(with_cost=False)[5]
+    ms = tot / args.steps
+    obs_sweeps = s.n_obs * rep["sweeps"]
+    # end to end: host arrays in, poses + per-observation costs out
+    pa = tuple(pinned(x) for x in a)
+    times = []
+    for i in range(1 + min(args.steps, 3)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rig_api.rig_solve(ctx, *pa, s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f, opts=opts)
+        if i:
+            times.append(time.perf_counter() - t0)
+    e2e_t = float(np.mean(times))
+    import oracle
+
+    oracle.build()
+    t0 = time.perf_counter()
+    ref = oracle.rig_solve(*a, s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    cpu_dt = time.perf_counter() - t0
+    F, C, P = 1000, 4, 187
+    alg = 12.0 * s.n_obs + 12.0 * F * P + (56 + 8 * (21 + 36 * (C - 1) + 6)) * F
+    line = {
+        "metric": "residual+Jacobian observations/s (full LM solve)", "value": obs_sweeps / (ms * 1e-3), "unit": "obs/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: rig extrinsics (ExtrinsicsCalibrator::Optimize), 4 cameras x 1000 frames "
+                               "x 187 shared board points, Huber loss", "cameras": C, "frames": F, "points_per_frame": P,
+                   "cache": "inputs smaller than L2: L2-resident after the first sweep (roofline not meaningful)"},
+        "lm_iterations_per_s": rep["iterations"] / (ms * 1e-3),
+        "solve": {k: rep[k] for k in ("iterations", "sweeps", "rejected", "termination", "rms", "gradient_norm")},
+        "roofline": {"kernel": "k_rig_sweep", "bound": "hbm", "achieved": None, "peak": measured_peaks()[0], "unit": "GB/s",
+                     "frac": None, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                     "note": "9 MB working set is L2-resident: no HBM fraction quoted (SURVEY 8d)"},
+        "cpu_baseline": {"value": s.n_obs * ref[5]["sweeps"] / cpu_dt, "unit": "obs/s", "cores": oracle.num_threads(),
+                         "kind": "port", "sample": "the full C3 problem, full LM solve", "seconds": cpu_dt},
+        "e2e": {"value": obs_sweeps / e2e_t, "unit": "obs/s", "h2d_bytes_per_step": int(sum(x.nbytes for x in a)),
+                "d2h_bytes_per_step": int(8 * s.n_obs + 56 * (F + C)), "ms_per_step": e2e_t * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    prob.close()
+    ctx.close()
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -431,11 +508,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS) + ["c3"])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "c3":
+        if args.impl == "reference" or args.gpus != 1:
+            raise SystemExit("--workload c3 (rig) is a single-GPU line of the GPU arm (its CPU port is timed beside it)")
+        run_rig(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

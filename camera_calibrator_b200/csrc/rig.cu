@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -621,6 +622,10 @@ struct ccg_rig_problem {
   std::vector<int64_t> perm;  // sorted position -> caller's observation index
   double meas_scale = 0.0;
   double huber_a = (double)(3.0f / 500.0f);  // of the last run (final per-observation cost pass)
+  cudaGraphExec_t graph_exec = nullptr;      // one LM iteration, see rig_run
+  LmParams graph_params;
+  int graph_kernels = 0, graph_allreduces = 0;
+  bool one_shot = false;                     // created by ccg_rig_solve: runs once, no graph instantiation
 };
 
 namespace {
@@ -644,6 +649,7 @@ int rig_alloc(ccg_rig_problem* p, T** out, size_t n) {
 void rig_free(ccg_rig_problem* p) {
   if (!p) return;
   if (p->ctx) cudaSetDevice(p->ctx->device);
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   for (void* a : p->allocs) pool_free(p->ctx, a);
   delete p;
 }
@@ -828,11 +834,41 @@ int rig_run(ccg_rig_problem* p, const ccg_opts& opts, ccg_timing* timing) {
   cudaEventRecord(ctx->events[e0], ctx->stream);
   CCG_TRY(rig_reset(p, P));
   CCG_TRY(rig_sweep_decide(p, P, prof, nullptr, &nar));
+  // one LM iteration (six launches, allreduces included) replayed as a CUDA graph when no
+  // per-kernel events are requested and the problem object is reused (CCG_NO_GRAPH=1 disables)
+  static const bool no_graph = getenv("CCG_NO_GRAPH") != nullptr;
+  const bool use_graph = !prof.on && !no_graph && !p->one_shot;
+  if (use_graph && (!p->graph_exec || std::memcmp(&p->graph_params, &P, sizeof(P)) != 0)) {
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    p->graph_exec = nullptr;
+    cudaGraph_t g = nullptr;
+    const int64_t l0 = ctx->launches;
+    const int a0 = nar;
+    CCG_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    int rc = rig_schur_solve(p, P, prof, &nar);
+    if (rc == CCG_OK) rc = rig_sweep_decide(p, P, prof, nullptr, &nar);
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    p->graph_kernels = (int)(ctx->launches - l0);
+    p->graph_allreduces = nar - a0;
+    ctx->launches = l0;
+    nar = a0;
+    if (rc != CCG_OK) return rc;
+    if (e != cudaSuccess) return set_error(ctx, CCG_ERR_CUDA, "cudaStreamEndCapture", e);
+    CCG_CUDA(ctx, cudaGraphInstantiate(&p->graph_exec, g, 0));
+    cudaGraphDestroy(g);
+    p->graph_params = P;
+  }
   int done = 0;
   for (int it = 0; it <= opts.max_iterations * 2 + 64; ++it) {
-    CCG_TRY(rig_schur_solve(p, P, prof, &nar));
-    if (done >= 1) break;
-    CCG_TRY(rig_sweep_decide(p, P, prof, nullptr, &nar));
+    if (use_graph && done < 1) {
+      CCG_CUDA(ctx, cudaGraphLaunch(p->graph_exec, ctx->stream));
+      ctx->launches += p->graph_kernels;
+      nar += p->graph_allreduces;
+    } else {
+      CCG_TRY(rig_schur_solve(p, P, prof, &nar));
+      if (done >= 1) break;
+      CCG_TRY(rig_sweep_decide(p, P, prof, nullptr, &nar));
+    }
     if ((it & 3) == 3) {
       CCG_CUDA(ctx, cudaMemcpyAsync(ctx->h_poll, p->dev.n_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -982,6 +1018,7 @@ int ccg_rig_solve(ccg_ctx* ctx, const float* u, const float* v, const int32_t* o
   int rc = ccg_rig_create(ctx, u, v, obs_cam, obs_point, frame_offsets, n_frames, Xw, n_points, n_cams, q_c,
                           t_c, cam_frozen, q_f, t_f, 0, &p);
   if (rc != CCG_OK) return rc;
+  p->one_shot = true;
   rc = ccg_rig_run(p, opts, nullptr);
   if (rc == CCG_OK) rc = rig_download(p, q_c, t_c, q_f, t_f, obs_cost, report);
   rig_free(p);
