@@ -116,6 +116,39 @@ class Context:
         self._check(rc, "ccg_intrinsics_solve_batch")
         return intr, q, t, [r.asdict() for r in reps]
 
+    def intrinsics_estimate(self, u, v, X, Y, Z, view_offsets, const_mask=0, opts=None, problem_offsets=None):
+        """Calibrator::Estimate: closed-form initialisation on the device + LM solve.
+        Returns (intr[9] or [B,9], q[V,4], t[V,3], report(s), intr_init)."""
+        u, v, X, Y, Z = map(f32, (u, v, X, Y, Z))
+        off = i64(view_offsets)
+        nv = len(off) - 1
+        o = opts if opts is not None else default_opts()
+        q = np.zeros((nv, 4))
+        t = np.zeros((nv, 3))
+        if problem_offsets is None:
+            intr = np.zeros(9)
+            init = np.zeros(9)
+            rep = Report()
+            rc = _ccg.lib().ccg_intrinsics_estimate(
+                self._h, ptr(u, C.c_float), ptr(v, C.c_float), ptr(X, C.c_float), ptr(Y, C.c_float),
+                ptr(Z, C.c_float), ptr(off, C.c_int64), C.c_int64(nv), ptr(intr, C.c_double),
+                ptr(q, C.c_double), ptr(t, C.c_double), ptr(init, C.c_double), C.c_uint32(const_mask),
+                C.byref(o), C.byref(rep))
+            self._check(rc, "ccg_intrinsics_estimate")
+            return intr, q, t, rep.asdict(), init
+        poff = i64(problem_offsets)
+        nb = len(poff) - 1
+        intr = np.zeros((nb, 9))
+        init = np.zeros((nb, 9))
+        reps = (Report * nb)()
+        rc = _ccg.lib().ccg_intrinsics_estimate_batch(
+            self._h, ptr(u, C.c_float), ptr(v, C.c_float), ptr(X, C.c_float), ptr(Y, C.c_float),
+            ptr(Z, C.c_float), ptr(off, C.c_int64), C.c_int64(nv), ptr(poff, C.c_int64), C.c_int64(nb),
+            ptr(intr, C.c_double), ptr(q, C.c_double), ptr(t, C.c_double), ptr(init, C.c_double),
+            C.c_uint32(const_mask), C.byref(o), reps)
+        self._check(rc, "ccg_intrinsics_estimate_batch")
+        return intr, q, t, [r.asdict() for r in reps], init
+
     def intrinsics_eval(self, u, v, X, Y, Z, view_offsets, intr, q, t, hessian_fp64=0):
         """One sweep at the given point.  hessian_fp64: 0 tensor-core TF32 J'J (default sweep), 1 all FP64,
         2 FP32 FFMA J'J (ccg_opts.hessian_fp64)."""

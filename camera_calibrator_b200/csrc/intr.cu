@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep(IntrDev d, double
 }  // namespace ccg
 #include "intr_mixed.cuh"
 #include "intr_tc.cuh"
+#include "intr_init.cuh"
 namespace ccg {
 
 // --------------------------------------------------------------------------
@@ -1316,6 +1317,68 @@ int ccg_intrinsics_solve(ccg_ctx* ctx, const float* u, const float* v, const flo
   const int64_t poff[2] = {0, n_views};
   return ccg_intrinsics_solve_batch(ctx, u, v, X, Y, Z, view_offsets, n_views, poff, 1, intr, q, t,
                                     const_intr_mask, opts, report);
+}
+
+// Estimate = closed-form initialisation on the device + LM solve, the whole of Calibrator::Estimate
+// (reference src/calibrator.cpp:47-68) behind one call: the observations are uploaded once.
+int ccg_intrinsics_estimate_batch(ccg_ctx* ctx, const float* u, const float* v, const float* X,
+                                  const float* Y, const float* Z, const int64_t* view_offsets,
+                                  int64_t n_views, const int64_t* problem_offsets, int64_t n_problems,
+                                  double* intr, double* q, double* t, double* intr_init,
+                                  uint32_t const_intr_mask, const ccg_opts* opts, ccg_report* reports) {
+  if (!ctx || !intr || n_problems < 1 || n_views < 0) return CCG_ERR_BAD_ARG;
+  const int64_t one[2] = {0, n_views};
+  if (!problem_offsets) {
+    if (n_problems != 1) return set_error(ctx, CCG_ERR_BAD_ARG, "problem_offsets required");
+    problem_offsets = one;
+  }
+  // placeholders: the init kernels overwrite the starting point on the device
+  std::vector<double> intr0((size_t)n_problems * 9, 0.0), q0((size_t)std::max<int64_t>(n_views, 1) * 4, 0.0),
+      t0((size_t)std::max<int64_t>(n_views, 1) * 3, 0.0);
+  ccg_intr_problem* p = nullptr;
+  int rc = ccg_intrinsics_create(ctx, u, v, X, Y, Z, view_offsets, n_views, problem_offsets, n_problems,
+                                 intr0.data(), q0.data(), t0.data(), const_intr_mask, 0, &p);
+  if (rc != CCG_OK) return rc;
+  p->one_shot = true;
+  auto body = [&]() -> int {
+    cudaStream_t st = ctx->stream;
+    double* d_H = nullptr;
+    int* d_status = nullptr;
+    CCG_TRY(dev_alloc(p, &d_H, (size_t)std::max<int64_t>(n_views, 1) * 9));
+    CCG_TRY(dev_alloc(p, &d_status, (size_t)n_problems));
+    int64_t max_views = 1;
+    for (int64_t b = 0; b < n_problems; ++b)
+      max_views = std::max(max_views, problem_offsets[b + 1] - problem_offsets[b]);
+    if (n_views > 0)
+      k_init_homography<<<(int)((n_views + kInitWarps - 1) / kInitWarps), kInitWarps * 32, 0, st>>>(p->dev, n_views, d_H);
+    k_init_zhang<<<(int)n_problems, 256, 0, st>>>(d_H, p->d_problem_off, p->d_meas_scale, p->d_intr0, d_status);
+    k_init_extrinsics<<<dim3((unsigned)((max_views + 127) / 128), (unsigned)n_problems), 128, 0, st>>>(
+        d_H, p->d_problem_off, (int)n_problems, p->d_intr0, p->d_pose0);
+    ctx->launches += 3;
+    std::vector<int> status((size_t)n_problems, 0);
+    CCG_CUDA(ctx, cudaMemcpyAsync(status.data(), d_status, sizeof(int) * n_problems, cudaMemcpyDeviceToHost, st));
+    if (intr_init)
+      CCG_CUDA(ctx, cudaMemcpyAsync(intr_init, p->d_intr0, sizeof(double) * 9 * n_problems, cudaMemcpyDeviceToHost, st));
+    CCG_CUDA(ctx, cudaStreamSynchronize(st));
+    CCG_CUDA(ctx, cudaGetLastError());
+    for (int64_t b = 0; b < n_problems; ++b)
+      if (status[(size_t)b] != 0)
+        return set_error(ctx, status[(size_t)b], "closed-form initialisation failed (fewer than 3 usable views, or no real solution for K)");
+    CCG_TRY(ccg_intrinsics_run(p, opts, nullptr));
+    return download_problem(p, intr, q, t, reports);
+  };
+  rc = body();
+  free_problem(p);
+  return rc;
+}
+
+int ccg_intrinsics_estimate(ccg_ctx* ctx, const float* u, const float* v, const float* X, const float* Y,
+                            const float* Z, const int64_t* view_offsets, int64_t n_views, double* intr,
+                            double* q, double* t, double* intr_init, uint32_t const_intr_mask,
+                            const ccg_opts* opts, ccg_report* report) {
+  const int64_t poff[2] = {0, n_views};
+  return ccg_intrinsics_estimate_batch(ctx, u, v, X, Y, Z, view_offsets, n_views, poff, 1, intr, q, t, intr_init,
+                                       const_intr_mask, opts, report);
 }
 
 int ccg_intrinsics_eval(ccg_ctx* ctx, const float* u, const float* v, const float* X,

@@ -4,6 +4,7 @@
 // (calibrator.cpp:326-335).
 #include "calibrator.hh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <stdexcept>
@@ -47,24 +48,96 @@ void Calibrator::EstimateOpenCv(const std::vector<Points2D>&, const std::vector<
       "of this build (out of scope). Use Estimate().");
 }
 
+namespace {
+SolveReport ToReport(const ccg_report& rep) {
+  SolveReport r;
+  r.iterations = rep.iterations;
+  r.accepted = rep.accepted;
+  r.rejected = rep.rejected;
+  r.sweeps = rep.sweeps;
+  r.termination = rep.termination;
+  r.initial_cost = rep.initial_cost;
+  r.final_cost = rep.final_cost;
+  r.gradient_norm = rep.gradient_norm;
+  r.rms = rep.rms;
+  return r;
+}
+}  // namespace
+
+namespace {
+// float32 API arrays -> the SoA the C-ABI takes (the packing of calibrator.cpp:283-303)
+void PackObservations(const std::vector<Points2D>& img, const std::vector<Points3D>& world, const char* who,
+                      std::vector<int64_t>* off, std::vector<float>* u, std::vector<float>* v,
+                      std::vector<float>* X, std::vector<float>* Y, std::vector<float>* Z) {
+  const size_t n_img = img.size();
+  off->assign(n_img + 1, 0);
+  for (size_t i = 0; i < n_img; ++i) {
+    if (img[i].size() != world[i].size())
+      throw std::invalid_argument(std::string(who) + ": point counts differ in a view");
+    (*off)[i + 1] = (*off)[i] + (int64_t)img[i].size();
+  }
+  const size_t n = (size_t)(*off)[n_img];
+  u->resize(n); v->resize(n); X->resize(n); Y->resize(n); Z->resize(n);
+  for (size_t i = 0; i < n_img; ++i) {
+    size_t o = (size_t)(*off)[i];
+    for (size_t j = 0; j < img[i].size(); ++j, ++o) {
+      (*u)[o] = img[i][j].x();
+      (*v)[o] = img[i][j].y();
+      (*X)[o] = world[i][j].x();
+      (*Y)[o] = world[i][j].y();
+      (*Z)[o] = world[i][j].z();
+    }
+  }
+}
+}  // namespace
+
 void Calibrator::Estimate(const std::vector<Points2D>& in_img_points,
                           const std::vector<Points3D>& in_world_points) {
   if (in_img_points.size() != in_world_points.size())
     throw std::invalid_argument("Calibrator::Estimate: image/world view counts differ");
-  std::vector<Matrix3> Hs;
-  Hs.reserve(in_img_points.size());
-  for (size_t i = 0; i < in_img_points.size(); ++i)
-    Hs.push_back(EstimateHomography(in_world_points[i], in_img_points[i]));
-  K_ = EstimateKFromHomographies(Hs);
-  std::vector<Quaternion> qs;
-  std::vector<Point3D> ts;
-  const Matrix3 K_inv = K_.inverse();
-  for (const auto& H : Hs) {
-    const auto [R, t] = RecoverExtrinsics(K_inv, H);
-    qs.emplace_back(R);
-    ts.push_back(t);
+  bool zero_dist = true;
+  for (int k = 0; k < 5; ++k) zero_dist = zero_dist && dist_(k) == 0.0f;
+  if (!zero_dist) {
+    // a caller-set distortion is the starting point of the solve (calibrator.cpp:262-266): keep the
+    // reference's literal sequence, closed forms on the host, then Optimize
+    std::vector<Matrix3> Hs;
+    Hs.reserve(in_img_points.size());
+    for (size_t i = 0; i < in_img_points.size(); ++i)
+      Hs.push_back(EstimateHomography(in_world_points[i], in_img_points[i]));
+    K_ = EstimateKFromHomographies(Hs);
+    std::vector<Quaternion> qs;
+    std::vector<Point3D> ts;
+    const Matrix3 K_inv = K_.inverse();
+    for (const auto& H : Hs) {
+      const auto [R, t] = RecoverExtrinsics(K_inv, H);
+      qs.emplace_back(R);
+      ts.push_back(t);
+    }
+    Optimize(in_img_points, in_world_points, qs, ts);
+    return;
   }
-  Optimize(in_img_points, in_world_points, qs, ts);
+  // default path: initialisation and solve on the device behind one call (the observations cross
+  // PCIe once; the per-view homographies are one warp each instead of a serial SVD loop)
+  const size_t n_img = in_img_points.size();
+  std::vector<int64_t> off;
+  std::vector<float> u, v, X, Y, Z;
+  PackObservations(in_img_points, in_world_points, "Calibrator::Estimate", &off, &u, &v, &X, &Y, &Z);
+  std::vector<double> q(4 * std::max<size_t>(n_img, 1)), t(3 * std::max<size_t>(n_img, 1));
+  double intr[NUM_INTR], init[NUM_INTR];
+  uint32_t mask = 0;
+  for (int idx : constant_intrinsics_)
+    if (idx >= 0 && idx < NUM_INTR) mask |= 1u << idx;
+  ccg_opts opts;
+  ccg_default_opts(&opts);
+  opts.max_iterations = 100;  // calibrator.cpp:319
+  ccg_report rep;
+  ccg_ctx* ctx = HostContext();
+  const int rc = ccg_intrinsics_estimate(ctx, u.data(), v.data(), X.data(), Y.data(), Z.data(), off.data(),
+                                         (int64_t)n_img, intr, q.data(), t.data(), init, mask, &opts, &rep);
+  if (rc != CCG_OK)
+    throw std::runtime_error(std::string("Calibrator::Estimate: ") + ccg_status_string(rc) + " " +
+                             ccg_last_error(ctx));
+  StoreResult(ToReport(rep), intr, q.data(), t.data(), n_img);
 }
 
 void Calibrator::Optimize(const std::vector<Points2D>& in_img_points,
@@ -73,14 +146,9 @@ void Calibrator::Optimize(const std::vector<Points2D>& in_img_points,
   const size_t n_img = in_img_points.size();
   if (n_img != in_world_points.size() || n_img != qs.size() || n_img != ts.size())
     throw std::invalid_argument("Calibrator::Optimize: per-view argument sizes differ");
-  std::vector<int64_t> off(n_img + 1, 0);
-  for (size_t i = 0; i < n_img; ++i) {
-    if (in_img_points[i].size() != in_world_points[i].size())
-      throw std::invalid_argument("Calibrator::Optimize: point counts differ in a view");
-    off[i + 1] = off[i] + (int64_t)in_img_points[i].size();
-  }
-  const size_t n = (size_t)off[n_img];
-  std::vector<float> u(n), v(n), X(n), Y(n), Z(n);
+  std::vector<int64_t> off;
+  std::vector<float> u, v, X, Y, Z;
+  PackObservations(in_img_points, in_world_points, "Calibrator::Optimize", &off, &u, &v, &X, &Y, &Z);
   std::vector<double> q(4 * n_img), t(3 * n_img);
   for (size_t i = 0; i < n_img; ++i) {
     q[4 * i + 0] = qs[i].w();
@@ -90,14 +158,6 @@ void Calibrator::Optimize(const std::vector<Points2D>& in_img_points,
     t[3 * i + 0] = ts[i].x();
     t[3 * i + 1] = ts[i].y();
     t[3 * i + 2] = ts[i].z();
-    size_t o = (size_t)off[i];
-    for (size_t j = 0; j < in_img_points[i].size(); ++j, ++o) {
-      u[o] = in_img_points[i][j].x();
-      v[o] = in_img_points[i][j].y();
-      X[o] = in_world_points[i][j].x();
-      Y[o] = in_world_points[i][j].y();
-      Z[o] = in_world_points[i][j].z();
-    }
   }
   double intr[NUM_INTR];
   intr[OFF_FX] = K_(0, 0);
@@ -123,22 +183,19 @@ void Calibrator::Optimize(const std::vector<Points2D>& in_img_points,
   if (rc != CCG_OK)
     throw std::runtime_error(std::string("Calibrator::Optimize: ") + ccg_status_string(rc) + " " +
                              ccg_last_error(ctx));
-  report_.iterations = rep.iterations;
-  report_.accepted = rep.accepted;
-  report_.rejected = rep.rejected;
-  report_.sweeps = rep.sweeps;
-  report_.termination = rep.termination;
-  report_.initial_cost = rep.initial_cost;
-  report_.final_cost = rep.final_cost;
-  report_.gradient_norm = rep.gradient_norm;
-  report_.rms = rep.rms;
+  StoreResult(ToReport(rep), intr, q.data(), t.data(), n_img);
+}
+
+void Calibrator::StoreResult(const SolveReport& rep, const double* intr, const double* q, const double* t,
+                             size_t n_img) {
+  report_ = rep;
   opt_q_.resize(n_img);
   opt_t_.resize(n_img);
   for (size_t i = 0; i < n_img; ++i) {
     opt_q_[i] = {q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]};
     opt_t_[i] = {t[3 * i], t[3 * i + 1], t[3 * i + 2]};
   }
-  // Put params back (float32, K and distortion only)
+  // Put params back (float32, K and distortion only; calibrator.cpp:326-335)
   K_(0, 0) = static_cast<float>(intr[OFF_FX]);
   K_(1, 1) = static_cast<float>(intr[OFF_FY]);
   K_(0, 2) = static_cast<float>(intr[OFF_PX]);

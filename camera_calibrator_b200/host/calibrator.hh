@@ -29,7 +29,9 @@ class Calibrator {
   // part of this build; the call throws std::runtime_error (out of scope).
   void EstimateOpenCv(const std::vector<Points2D>& in_img_points, const std::vector<Points3D>& in_world_points);
 
-  // closed-form initialisation (homographies -> K -> per-view pose) then Optimize (calibrator.cpp:47-68)
+  // closed-form initialisation (homographies -> K -> per-view pose) then Optimize (calibrator.cpp:47-68);
+  // both run on the device behind ccg_intrinsics_estimate (host closed forms only when a distortion was
+  // set beforehand, which the reference would use as the starting point)
   void Estimate(const std::vector<Points2D>& in_img_points, const std::vector<Points3D>& in_world_points);
 
   // LM over 9 intrinsics + one pose per view (calibrator.cpp:221-336).  As in the reference,
@@ -56,6 +58,7 @@ class Calibrator {
   void GetOptimizedPoses(std::vector<std::array<double, 4>>* qs, std::vector<std::array<double, 3>>* ts) const;
 
  private:
+  void StoreResult(const SolveReport& rep, const double* intr, const double* q, const double* t, size_t n_img);
   int width_;
   int height_;
   Matrix3 K_{Matrix3::Identity()};

@@ -131,12 +131,31 @@ int ccg_intrinsics_solve_batch(ccg_ctx* ctx, const float* u, const float* v, con
                                uint32_t const_intr_mask, const ccg_opts* opts,
                                ccg_report* reports);
 
+/* Calibrator::Estimate (reference src/calibrator.cpp:47-68) in one call: the closed-form
+ * initialisation (per-view DLT homography, Zhang's K with zero skew, per-view RecoverExtrinsics +
+ * FixRotationMatrix; reference src/geometry.cpp:70-203) runs on the device on the uploaded
+ * observations (world points are read as planar: X, Y), then the LM solve of ccg_intrinsics_solve.
+ * intr, q, t are OUTPUTS only (q, t may be NULL); intr_init (may be NULL) receives the closed-form
+ * starting point fx fy px py 0 0 0 0 0.  Needs at least 3 views with 4 or more points per problem
+ * (CCG_ERR_BAD_ARG otherwise); CCG_ERR_NOT_FINITE when the closed form has no real solution. */
+int ccg_intrinsics_estimate(ccg_ctx* ctx, const float* u, const float* v, const float* X,
+                            const float* Y, const float* Z, const int64_t* view_offsets,
+                            int64_t n_views, double* intr, double* q, double* t, double* intr_init,
+                            uint32_t const_intr_mask, const ccg_opts* opts, ccg_report* report);
+int ccg_intrinsics_estimate_batch(ccg_ctx* ctx, const float* u, const float* v, const float* X,
+                                  const float* Y, const float* Z, const int64_t* view_offsets,
+                                  int64_t n_views, const int64_t* problem_offsets,
+                                  int64_t n_problems, double* intr, double* q, double* t,
+                                  double* intr_init, uint32_t const_intr_mask, const ccg_opts* opts,
+                                  ccg_report* reports);
+
 /* One residual+Jacobian+normal-equation evaluation at the given parameters
  * (the blocks the LM loop consumes), for parity tests.  Any output may be NULL.
  *   res 2/obs | Vb 36/view (6x6) | Wb 54/view (6x9) | gvb 6/view | U 81 | gu 9 | cost 1
  * Tangent order per view: rotation (half-angle vector, Ceres QuaternionManifold
  * convention) then translation.  hessian_fp64 selects the sweep variant (see ccg_opts): with 0
- * V, W, U carry FP32 rounding (~1e-6 relative), res, gvb, gu, cost are FP64 in both. */
+ * V, W, U are TF32 tensor-core products (~1e-3 relative), with 2 FP32 (~1e-6); res, gvb, gu and
+ * cost are FP64 in every variant. */
 int ccg_intrinsics_eval(ccg_ctx* ctx, const float* u, const float* v, const float* X,
                         const float* Y, const float* Z, const int64_t* view_offsets,
                         int64_t n_views, const double* intr, const double* q, const double* t,
