@@ -116,6 +116,29 @@ class Context:
         self._check(rc, "ccg_intrinsics_solve_batch")
         return intr, q, t, [r.asdict() for r in reps]
 
+    def undistort(self, px, py, K, dist):
+        """Calibrator::Undistort on arrays: pixels -> undistorted normalised coordinates (float32)."""
+        px, py = f32(px), f32(py)
+        K32 = np.ascontiguousarray(K, dtype=np.float32).reshape(3, 3)
+        Kinv = np.ascontiguousarray(np.linalg.inv(K32.astype(np.float64)).astype(np.float32))
+        d5 = np.ascontiguousarray(dist, dtype=np.float32).reshape(5)
+        xn, yn = np.zeros_like(px), np.zeros_like(py)
+        self._check(_ccg.lib().ccg_undistort(self._h, ptr(px, C.c_float), ptr(py, C.c_float), C.c_int64(px.size),
+                                             ptr(Kinv, C.c_float), ptr(d5, C.c_float), ptr(xn, C.c_float),
+                                             ptr(yn, C.c_float)), "ccg_undistort")
+        return xn, yn
+
+    def distort(self, xn, yn, K, dist):
+        """Calibrator::Distort on arrays: normalised coordinates -> distorted pixels (float32)."""
+        xn, yn = f32(xn), f32(yn)
+        K32 = np.ascontiguousarray(K, dtype=np.float32).reshape(3, 3)
+        d5 = np.ascontiguousarray(dist, dtype=np.float32).reshape(5)
+        px, py = np.zeros_like(xn), np.zeros_like(yn)
+        self._check(_ccg.lib().ccg_distort(self._h, ptr(xn, C.c_float), ptr(yn, C.c_float), C.c_int64(xn.size),
+                                           ptr(K32, C.c_float), ptr(d5, C.c_float), ptr(px, C.c_float),
+                                           ptr(py, C.c_float)), "ccg_distort")
+        return px, py
+
     def intrinsics_estimate(self, u, v, X, Y, Z, view_offsets, const_mask=0, opts=None, problem_offsets=None):
         """Calibrator::Estimate: closed-form initialisation on the device + LM solve.
         Returns (intr[9] or [B,9], q[V,4], t[V,3], report(s), intr_init)."""

@@ -217,58 +217,45 @@ void Calibrator::ForceDistortionToConstant(const int distortion_idx) {
   constant_intrinsics_.insert(distortion_idx + static_cast<int>(OFF_K1));
 }
 
-namespace {
-template <typename T>
-inline void lens(T k1, T k2, T k3, T p1, T p2, T x, T y, T* xd, T* yd) {
-  const T r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
-  const T m = T(1) + k1 * r2 + k2 * r4 + k3 * r6;
-  *xd = x * m + T(2) * p1 * x * y + p2 * (r2 + T(2) * x * x);
-  *yd = y * m + T(2) * p2 * x * y + p1 * (r2 + T(2) * y * y);
-}
-}  // namespace
-
 Points2D Calibrator::Undistort(const Points2D& img_points) {
-  // The reference solves, per point, a 2-unknown least-squares problem with Ceres
-  // (DENSE_QR, <= 1000 iterations) starting from the distorted coordinates.  Here the
-  // same fixed point is found with damped Newton steps on the 2x2 system in double.
+  // The reference solves, per point, a 2-unknown least-squares problem with Ceres (DENSE_QR,
+  // <= 1000 iterations) starting from the distorted coordinates (calibrator.cpp:97-155).  The same
+  // fixed point is found on the device, one thread per point, with Newton steps on the 2x2 system
+  // in double (ccg_undistort).
   const Matrix3 K_inv = K_.inverse();
-  const double k1 = dist_(0), k2 = dist_(1), p1 = dist_(2), p2 = dist_(3), k3 = dist_(4);
-  Points2D out;
-  out.reserve(img_points.size());
-  for (const auto& p : img_points) {
-    const float w = K_inv(2, 0) * p.x() + K_inv(2, 1) * p.y() + K_inv(2, 2);
-    const double xt = (K_inv(0, 0) * p.x() + K_inv(0, 1) * p.y() + K_inv(0, 2)) / w;
-    const double yt = (K_inv(1, 0) * p.x() + K_inv(1, 1) * p.y() + K_inv(1, 2)) / w;
-    double x = xt, y = yt;
-    for (int it = 0; it < 1000; ++it) {
-      double xd, yd;
-      lens(k1, k2, k3, p1, p2, x, y, &xd, &yd);
-      const double ex = xd - xt, ey = yd - yt;
-      const double r2 = x * x + y * y, r4 = r2 * r2;
-      const double m = 1.0 + k1 * r2 + k2 * r4 + k3 * r4 * r2, mp = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
-      const double a = m + 2.0 * x * x * mp + 2.0 * p1 * y + 6.0 * p2 * x;
-      const double b = 2.0 * x * y * mp + 2.0 * p1 * x + 2.0 * p2 * y;
-      const double d = m + 2.0 * y * y * mp + 2.0 * p2 * x + 6.0 * p1 * y;
-      const double det = a * d - b * b;
-      if (!(std::fabs(det) > 1e-300)) break;
-      const double dx = (d * ex - b * ey) / det, dy = (a * ey - b * ex) / det;
-      x -= dx;
-      y -= dy;
-      if (std::fabs(dx) + std::fabs(dy) <= 1e-16 * (1.0 + std::fabs(x) + std::fabs(y))) break;
-    }
-    out.emplace_back((float)x, (float)y);
+  const size_t n = img_points.size();
+  std::vector<float> px(n), py(n), xn(n), yn(n);
+  for (size_t i = 0; i < n; ++i) {
+    px[i] = img_points[i].x();
+    py[i] = img_points[i].y();
   }
+  const float dist[5] = {dist_(0), dist_(1), dist_(2), dist_(3), dist_(4)};
+  ccg_ctx* ctx = HostContext();
+  const int rc = ccg_undistort(ctx, px.data(), py.data(), (int64_t)n, K_inv.m, dist, xn.data(), yn.data());
+  if (rc != CCG_OK)
+    throw std::runtime_error(std::string("Calibrator::Undistort: ") + ccg_status_string(rc) + " " + ccg_last_error(ctx));
+  Points2D out;
+  out.reserve(n);
+  for (size_t i = 0; i < n; ++i) out.emplace_back(xn[i], yn[i]);
   return out;
 }
 
 Points2D Calibrator::Distort(const Points2D& normalized_points) {
-  Points2D out;
-  out.reserve(normalized_points.size());
-  for (const auto& p : normalized_points) {
-    float xd, yd;  // float arithmetic, as the reference instantiates DistortPixels here
-    lens<float>(dist_(0), dist_(1), dist_(4), dist_(2), dist_(3), p.x(), p.y(), &xd, &yd);
-    out.emplace_back(K_(0, 0) * xd + K_(0, 2), K_(1, 1) * yd + K_(1, 2));
+  // float32 lens model + K (calibrator.cpp:157-166), one thread per point (ccg_distort)
+  const size_t n = normalized_points.size();
+  std::vector<float> xn(n), yn(n), px(n), py(n);
+  for (size_t i = 0; i < n; ++i) {
+    xn[i] = normalized_points[i].x();
+    yn[i] = normalized_points[i].y();
   }
+  const float dist[5] = {dist_(0), dist_(1), dist_(2), dist_(3), dist_(4)};
+  ccg_ctx* ctx = HostContext();
+  const int rc = ccg_distort(ctx, xn.data(), yn.data(), (int64_t)n, K_.m, dist, px.data(), py.data());
+  if (rc != CCG_OK)
+    throw std::runtime_error(std::string("Calibrator::Distort: ") + ccg_status_string(rc) + " " + ccg_last_error(ctx));
+  Points2D out;
+  out.reserve(n);
+  for (size_t i = 0; i < n; ++i) out.emplace_back(px[i], py[i]);
   return out;
 }
 

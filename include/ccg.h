@@ -149,6 +149,17 @@ int ccg_intrinsics_estimate_batch(ccg_ctx* ctx, const float* u, const float* v, 
                                   double* intr_init, uint32_t const_intr_mask, const ccg_opts* opts,
                                   ccg_report* reports);
 
+/* Batched lens model of calibrator::Calibrator, host buffers in and out.
+ * ccg_undistort: pixels -> undistorted normalised coordinates (Calibrator::Undistort, reference
+ *   src/calibrator.cpp:97-155); K_inv = the float32 inverse of K, row-major, as the class forms it;
+ *   dist = k1 k2 p1 p2 k3.
+ * ccg_distort: normalised coordinates -> distorted pixels (Calibrator::Distort, calibrator.cpp:157-166);
+ *   K row-major float32 (zero skew). */
+int ccg_undistort(ccg_ctx* ctx, const float* px, const float* py, int64_t n, const float K_inv[9],
+                  const float dist[5], float* xn, float* yn);
+int ccg_distort(ccg_ctx* ctx, const float* xn, const float* yn, int64_t n, const float K[9],
+                const float dist[5], float* px, float* py);
+
 /* One residual+Jacobian+normal-equation evaluation at the given parameters
  * (the blocks the LM loop consumes), for parity tests.  Any output may be NULL.
  *   res 2/obs | Vb 36/view (6x6) | Wb 54/view (6x9) | gvb 6/view | U 81 | gu 9 | cost 1

@@ -196,3 +196,35 @@ def test_estimate_needs_three_views(ctx):
     d = oracle.datagen_planar(2, 54)
     with pytest.raises(cc.CcgError):
         ctx.intrinsics_estimate(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets)
+
+
+def test_lens_kernels_match_float64_model(ctx):
+    """ccg_distort against the float32 model evaluated in numpy (bit-exact: same operations, no
+    contraction) and ccg_undistort against the float64 root of the lens equations, on 1e6 points."""
+    rng = np.random.default_rng(3)
+    n = 1_000_000
+    K = np.array([[1000, 0, 800], [0, 990, 500], [0, 0, 1]], np.float32)
+    dist = np.array([-4e-2, 5e-4, 1e-3, 2e-5, -3e-4], np.float32)
+    xn = rng.uniform(-0.7, 0.7, n).astype(np.float32)
+    yn = rng.uniform(-0.45, 0.45, n).astype(np.float32)
+    k1, k2, p1, p2, k3 = dist
+    two = np.float32(2.0)
+    r2 = xn * xn + yn * yn
+    r4 = r2 * r2
+    r6 = r4 * r2
+    m = np.float32(1.0) + k1 * r2 + k2 * r4 + k3 * r6
+    xd = xn * m + two * p1 * xn * yn + p2 * (r2 + two * xn * xn)
+    yd = yn * m + two * p2 * xn * yn + p1 * (r2 + two * yn * yn)
+    pu, pv = ctx.distort(xn, yn, K, dist)
+    assert np.array_equal(pu, K[0, 0] * xd + K[0, 2]) and np.array_equal(pv, K[1, 1] * yd + K[1, 2])
+    bx, by = ctx.undistort(pu, pv, K, dist)
+    # pixels are float32 (ulp 6e-5 px at 1e3 px = 6e-8 normalised): the round trip is exact to a few float32 ulp
+    assert np.max(np.abs(bx - xn)) < 1e-6 and np.max(np.abs(by - yn)) < 1e-6
+    # and the returned point IS a root of the float64 model for the given float32 pixels
+    x, y = bx.astype(np.float64), by.astype(np.float64)
+    d = dist.astype(np.float64)
+    r2 = x * x + y * y
+    mm = 1 + d[0] * r2 + d[1] * r2 ** 2 + d[4] * r2 ** 3
+    fx = (x * mm + 2 * d[2] * x * y + d[3] * (r2 + 2 * x * x)) * float(K[0, 0]) + float(K[0, 2])
+    fy = (y * mm + 2 * d[3] * x * y + d[2] * (r2 + 2 * y * y)) * float(K[1, 1]) + float(K[1, 2])
+    assert np.max(np.abs(fx - pu)) < 3e-4 and np.max(np.abs(fy - pv)) < 3e-4  # float32 rounding of the output (6e-8 x 1e3 px) and of the pixels

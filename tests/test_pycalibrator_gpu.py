@@ -131,3 +131,20 @@ def test_extrinsics_calibrator_optimize_matches_oracle(pc, tmp_path):
     e3.Optimize()
     for c in range(3):
         assert np.max(np.abs(e3.GetCameraTRig(c) - e.GetCameraTRig(c))) <= 1e-6
+
+
+def test_calibrator_lens_round_trip(pc):
+    """Distort then Undistort (calibrator.cpp:97-166) through the reference-facing class."""
+    c = pc.Calibrator(1600, 1000)
+    K = np.array([[1000, 0, 800], [0, 1000, 500], [0, 0, 1]], np.float32)
+    dist = np.array([-4e-2, 5e-4, 1e-3, 2e-5, -3e-4], np.float32)
+    c.SetK(K=K)
+    c.SetDistortion(distortion=dist)
+    rng = np.random.default_rng(0)
+    norm = rng.uniform(-0.5, 0.5, (50, 2)).astype(np.float32)
+    px = c.Distort(normalized_points=norm)
+    back = c.Undistort(img_points=px)
+    assert px.shape == (50, 2) and back.shape == (50, 2)
+    assert np.max(np.abs(back - norm)) < 2e-6  # float32 pixels in, float32 out
+    # lists of rows work like the reference's stl+eigen casters
+    assert np.allclose(c.Distort([[0.1, 0.2], [0.0, 0.0]])[1], [800, 500])
