@@ -374,10 +374,10 @@ def run_ours(args):
     # ---- device-resident solves: W warm-up, K timed
     for _ in range(args.warmup):
         prob.run(opts)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # before the barrier: spawning the sampler must not skew rank 0 against the others
+    barrier()
     launches0 = ctx.kernel_launches()
     tot_ms = 0.0
     n_allreduce = 0
