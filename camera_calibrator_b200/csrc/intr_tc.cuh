@@ -33,9 +33,11 @@ constexpr int kTcD = CCG_TC_D;     // FP64-role warps (the first kTcD warps of t
 constexpr int kTcJ = kTcWarps - kTcD;  // Jacobian/tensor-role warps
 constexpr int kTcRow = 20;         // floats per Jacobian row in the tile (16 + 4: conflict-free STS.128 and LDS.64)
 constexpr int kTcTile = 64 * kTcRow;  // one 32-observation tile; every warp owns two (double buffer)
-constexpr int kTcStages = 3;          // observation chunks in flight per warp (cp.async ring)
-constexpr int kTcStage = 5 * 32;      // floats per staged chunk: u v X Y Z of 32 observations
-constexpr int kTcRing = kTcStages * kTcStage;  // floats per warp: the observation ring
+constexpr int kTcSlots = 256;         // observations the circular staging buffer of a warp holds (8 granules of 32)
+constexpr int kTcAhead = 2;           // granules requested beyond the one being consumed
+constexpr int kTcBatch = 16;          // views whose poses and offsets a warp stages at a time
+// floats per warp: u v X Y Z circular buffers | 16 poses (12 doubles each) | 17 view offsets (int)
+constexpr int kTcRing = 5 * kTcSlots + kTcBatch * 24 + 32;
 // dynamic shared memory: per warp a 64-double partial and a 3-stage observation ring; per
 // Jacobian warp two tiles
 constexpr size_t kTcSmem = sizeof(double) * kTcWarps * kSweepPart +
@@ -245,40 +247,90 @@ __device__ __forceinline__ void tc_contract(const float* tile, int g, int tig, i
   }
 }
 
-// Asynchronous prefetch of one 32-observation chunk into the warp's staging ring (LDGSTS: no
-// registers are held while the loads are in flight, so ptxas cannot sink them next to their use -
-// it did exactly that with plain prefetch loads).  Lanes past the end of the view zero-fill.
+// ---------------------------------------------------------------------------------------------
+// Observation stream of a role warp.  A warp owns a CONTIGUOUS range of views, so its observations
+// are one contiguous stream in the SoA arrays.  The stream is fetched in 32-observation granules
+// (cp.async, LDGSTS: no registers are held while the loads are in flight - ptxas sank plain
+// prefetch loads next to their use) into a circular buffer of 256 observations per array, indexed
+// by the position in the stream modulo 256 - independent of where views begin and end.  The
+// consumer works on view-aligned chunks; before a chunk it makes sure the stream is requested
+// kTcAhead granules beyond the chunk's last observation and that the granule holding that
+// observation has landed (one commit group per granule, groups complete in order).  The HBM
+// latency is therefore exposed once per work item and warp, not once per view.
 // NARR = 5: u v X Y Z (FP64 role), NARR = 3: X Y Z (Jacobian role; the other role's copy of the
-// same lines is an L1/L2 hit, HBM traffic stays 20 B per observation).  One commit group per
-// chunk, so "wait_group kTcStages - 1" means "the chunk I am about to consume has landed".
+// same lines is an L1/L2 hit, HBM traffic stays 20 B per observation).
+// ---------------------------------------------------------------------------------------------
 template <int NARR>
-__device__ __forceinline__ void tc_prefetch(float* stage, const IntrDev& d, int64_t idx, int64_t end, int lane) {
-  const bool valid = idx < end;
-  const int64_t o = valid ? idx : 0;
-  const int sz = valid ? 4 : 0;
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + lane);
-  if (NARR == 5) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(d.u + o), "r"(sz) : "memory");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128), "l"(d.v + o), "r"(sz) : "memory");
+struct TcStream {
+  const IntrDev& d;
+  float* ring;
+  int64_t base;   // first observation of the warp's range
+  int n;          // observations in the range
+  int g_issued;   // granules requested so far
+  int lane;
+  __device__ __forceinline__ TcStream(const IntrDev& d_, float* ring_, int64_t o_first, int64_t o_last, int lane_)
+      : d(d_), ring(ring_), base(o_first), n((int)(o_last - o_first)), g_issued(0), lane(lane_) {
+    // the head of the stream is requested at once: it travels together with the first batch of
+    // poses and offsets (one round trip instead of two before the first observation is touched)
+#pragma unroll
+    for (int i = 0; i <= kTcAhead; ++i) issue();
   }
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 256), "l"(d.X + o), "r"(sz) : "memory");
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 384), "l"(d.Y + o), "r"(sz) : "memory");
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 512), "l"(d.Z + o), "r"(sz) : "memory");
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
+  __device__ __forceinline__ void issue() {
+    const int rel = 32 * g_issued + lane;
+    const bool valid = rel < n;
+    const int64_t o = base + (valid ? rel : 0);
+    const int sz = valid ? 4 : 0;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (rel & (kTcSlots - 1)));
+    if (NARR == 5) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(d.u + o), "r"(sz) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4 * kTcSlots), "l"(d.v + o), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 8 * kTcSlots), "l"(d.X + o), "r"(sz) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 12 * kTcSlots), "l"(d.Y + o), "r"(sz) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 16 * kTcSlots), "l"(d.Z + o), "r"(sz) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    ++g_issued;
+  }
+  // the chunk whose last observation has stream position rel_last is about to be consumed
+  __device__ __forceinline__ void ensure(int rel_last) {
+    const int g_need = rel_last >> 5;
+    while (g_issued <= g_need + kTcAhead) issue();  // warp-uniform
+    asm volatile("cp.async.wait_group %0;" ::"n"(kTcAhead) : "memory");
+    __syncwarp();  // a lane reads what other lanes copied
+  }
+  __device__ __forceinline__ void take(ObsIn& L, int rel, bool valid) const {
+    const int slot = rel & (kTcSlots - 1);
+    L.valid = valid;
+    L.o = base + rel;
+    if (NARR == 5) {
+      L.mu = ring[slot];
+      L.mv = ring[kTcSlots + slot];
+    }
+    L.X = ring[2 * kTcSlots + slot];
+    L.Y = ring[3 * kTcSlots + slot];
+    L.Z = ring[4 * kTcSlots + slot];
+  }
+};
 
-template <int NARR>
-__device__ __forceinline__ void tc_take(ObsIn& L, const float* stage, int64_t idx, int64_t end, int lane) {
-  asm volatile("cp.async.wait_group %0;" ::"n"(kTcStages - 1) : "memory");
-  L.valid = idx < end;
-  L.o = idx;
-  if (NARR == 5) {
-    L.mu = stage[lane];
-    L.mv = stage[32 + lane];
+// Poses (rotation + translation, 12 doubles) and stream-relative observation offsets of the next
+// kTcBatch views of the warp, staged in shared memory with one blocking round trip per batch.
+__device__ __forceinline__ void tc_stage_batch(const IntrDev& d, float* ring, int vb, int nb, int64_t base, int lane) {
+  double* s_pose = reinterpret_cast<double*>(ring + 5 * kTcSlots);
+  int* s_off = reinterpret_cast<int*>(ring + 5 * kTcSlots + kTcBatch * 24);
+  __syncwarp();  // the previous batch is no longer being read
+  // 16 poses = 1536 B = 3 x 16 B per lane
+  const char* src = reinterpret_cast<const char*>(d.rt + (size_t)vb * 12);
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(s_pose);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int byte = (k * 32 + lane) * 16;
+    if (byte < nb * 96)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + byte), "l"(src + byte) : "memory");
   }
-  L.X = stage[64 + lane];
-  L.Y = stage[96 + lane];
-  L.Z = stage[128 + lane];
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (lane <= nb) s_off[lane] = (int)(d.view_off[vb + lane] - base);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -400,29 +452,33 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
     double gu[9], cost = 0.0;
 #pragma unroll
     for (int i = 0; i < 9; ++i) gu[i] = 0.0;
-    for (int v = it.v0 + warp; v < it.v1; v += kTcD) {
-      const int64_t o0 = d.view_off[v], o1 = d.view_off[v + 1];
-      tc_prefetch<5>(ring, d, o0 + lane, o1, lane);
-      tc_prefetch<5>(ring + kTcStage, d, o0 + 32 + lane, o1, lane);
+    // this warp's contiguous share of the item's views
+    const int nvw = it.v1 - it.v0;
+    const int vw0 = it.v0 + (int)((int64_t)nvw * warp / kTcD), vw1 = it.v0 + (int)((int64_t)nvw * (warp + 1) / kTcD);
+    const double* s_pose = reinterpret_cast<const double*>(ring + 5 * kTcSlots);
+    const int* s_off = reinterpret_cast<const int*>(ring + 5 * kTcSlots + kTcBatch * 24);
+    TcStream<5> strm(d, ring, d.view_off[vw0], d.view_off[vw1], lane);
+    for (int vb = vw0; vb < vw1; vb += kTcBatch) {
+     const int nb = min(kTcBatch, vw1 - vb);
+     tc_stage_batch(d, ring, vb, nb, strm.base, lane);
+     for (int vi = 0; vi < nb; ++vi) {
+      const int v = vb + vi;
+      const int r0 = s_off[vi], r1 = s_off[vi + 1];
       double R[9], t[3], gv[6];
       {
-        const double2* rt = reinterpret_cast<const double2*>(d.rt + (size_t)v * 12);
+        const double2* rt = reinterpret_cast<const double2*>(s_pose + vi * 12);
         const double2 a = rt[0], b = rt[1], c = rt[2], e = rt[3], f = rt[4], h = rt[5];
         R[0] = a.x; R[1] = a.y; R[2] = b.x; R[3] = b.y; R[4] = c.x; R[5] = c.y;
         R[6] = e.x; R[7] = e.y; R[8] = f.x; t[0] = f.y; t[1] = h.x; t[2] = h.y;
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) gv[i] = 0.0;
-      int st = 0;
-      for (int64_t ob = o0; ob < o1; ob += 32) {
-        const int st_free = st == 0 ? kTcStages - 1 : st - 1;  // the previous chunk's stage: consumed
-        tc_prefetch<5>(ring + st_free * kTcStage, d, ob + 64 + lane, o1, lane);
+      for (int rb = r0; rb < r1; rb += 32) {
+        strm.ensure(min(rb + 31, r1 - 1));
         ObsIn cur;
-        tc_take<5>(cur, ring + st * kTcStage, ob + lane, o1, lane);
+        strm.take(cur, min(rb + lane, r1 - 1), rb + lane < r1);
         tc_fp64_observation<RES>(d, K, R, t, cur, gu, gv, cost, res_out);
-        st = st == kTcStages - 1 ? 0 : st + 1;
       }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
       // per-view gradient: reduce over lanes, fix up the rotation part, store
       double tmp[8];
 #pragma unroll
@@ -438,6 +494,7 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
       if (lane == 1) out = 2.0 * (r - (t[2] * sw0 - t[0] * sw2));
       if (lane == 2) out = 2.0 * (r - (t[0] * sw1 - t[1] * sw0));
       if (lane < 6) d.blk[par ^ 1][(size_t)v * kBlk + 21 + lane] = out;
+     }
     }
     // lane-private sums -> the team's partial: [0] sum r^2 | [16..24] g_u
     double tmp[16];
@@ -457,13 +514,20 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
     TcConst32 K;
     K.fx = (float)s_k[0]; K.fy = (float)s_k[1];
     K.k1 = (float)s_k[4]; K.k2 = (float)s_k[5]; K.p1 = (float)s_k[6]; K.p2 = (float)s_k[7]; K.k3 = (float)s_k[8];
-    for (int v = it.v0 + (warp - kTcD); v < it.v1; v += kTcJ) {
-      const int64_t o0 = d.view_off[v], o1 = d.view_off[v + 1];
-      tc_prefetch<3>(ring, d, o0 + lane, o1, lane);
-      tc_prefetch<3>(ring + kTcStage, d, o0 + 32 + lane, o1, lane);
+    const int jw = warp - kTcD, nvw = it.v1 - it.v0;
+    const int vw0 = it.v0 + (int)((int64_t)nvw * jw / kTcJ), vw1 = it.v0 + (int)((int64_t)nvw * (jw + 1) / kTcJ);
+    const double* s_pose = reinterpret_cast<const double*>(ring + 5 * kTcSlots);
+    const int* s_off = reinterpret_cast<const int*>(ring + 5 * kTcSlots + kTcBatch * 24);
+    TcStream<3> strm(d, ring, d.view_off[vw0], d.view_off[vw1], lane);
+    for (int vb = vw0; vb < vw1; vb += kTcBatch) {
+     const int nb = min(kTcBatch, vw1 - vb);
+     tc_stage_batch(d, ring, vb, nb, strm.base, lane);
+     for (int vi = 0; vi < nb; ++vi) {
+      const int v = vb + vi;
+      const int r0 = s_off[vi], r1 = s_off[vi + 1];
       float Rf[9], tf[3];
       {
-        const double2* rt = reinterpret_cast<const double2*>(d.rt + (size_t)v * 12);
+        const double2* rt = reinterpret_cast<const double2*>(s_pose + vi * 12);
         const double2 a = rt[0], b = rt[1], c = rt[2], e = rt[3], f = rt[4], h = rt[5];
         Rf[0] = (float)a.x; Rf[1] = (float)a.y; Rf[2] = (float)b.x; Rf[3] = (float)b.y; Rf[4] = (float)c.x;
         Rf[5] = (float)c.y; Rf[6] = (float)e.x; Rf[7] = (float)e.y; Rf[8] = (float)f.x;
@@ -472,32 +536,29 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
       // product columns 0..7 (c0*) and 8..15 (c1*), two accumulator sets each
       float c0a[4] = {0.f, 0.f, 0.f, 0.f}, c0b[4] = {0.f, 0.f, 0.f, 0.f};
       float c1a[4] = {0.f, 0.f, 0.f, 0.f}, c1b[4] = {0.f, 0.f, 0.f, 0.f};
-      if (o1 > o0) {
+      if (r1 > r0) {
         // software pipeline over 32-observation chunks: while chunk j's rows are being computed,
-        // chunk j-1's tile is contracted (LDS + tensor pipe) and chunks j+1, j+2 are in flight
+        // chunk j-1's tile is contracted (LDS + tensor pipe) and the stream runs two granules ahead
         ObsIn cur;
         float4 ur[4], vr[4];
-        tc_prefetch<3>(ring + 2 * kTcStage, d, o0 + 64 + lane, o1, lane);
-        tc_take<3>(cur, ring, o0 + lane, o1, lane);
+        strm.ensure(min(r0 + 31, r1 - 1));
+        strm.take(cur, min(r0 + lane, r1 - 1), r0 + lane < r1);
         tc_fp32_rows(K, Rf, tf, cur.X, cur.Y, cur.Z, cur.valid, ur, vr);
         tc_store_rows(tiles, lane, ur, vr);
         __syncwarp();
-        int buf = 0, st = 1;  // tile that holds chunk j-1, stage that holds chunk j
-        int64_t ob = o0 + 32;
-        for (; ob < o1; ob += 32) {
-          const int st_free = st == 0 ? kTcStages - 1 : st - 1;  // chunk j-1's stage: consumed
-          tc_prefetch<3>(ring + st_free * kTcStage, d, ob + 64 + lane, o1, lane);
-          tc_take<3>(cur, ring + st * kTcStage, ob + lane, o1, lane);
+        int buf = 0;  // tile that holds chunk j-1
+        int rb = r0 + 32;
+        for (; rb < r1; rb += 32) {
+          strm.ensure(min(rb + 31, r1 - 1));
+          strm.take(cur, min(rb + lane, r1 - 1), rb + lane < r1);
           tc_contract<true>(tiles + buf * kTcTile, g, tig, 32, c0a, c0b, c1a, c1b);
           tc_fp32_rows(K, Rf, tf, cur.X, cur.Y, cur.Z, cur.valid, ur, vr);
           buf ^= 1;
-          st = st == kTcStages - 1 ? 0 : st + 1;
           tc_store_rows(tiles + buf * kTcTile, lane, ur, vr);
           __syncwarp();
         }
-        tc_contract<false>(tiles + buf * kTcTile, g, tig, (int)(o1 - (ob - 32)), c0a, c0b, c1a, c1b);
+        tc_contract<false>(tiles + buf * kTcTile, g, tig, r1 - (rb - 32), c0a, c0b, c1a, c1b);
       }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       // per-view epilogue: V, W blocks and the view's contribution to U
       double* blk = d.blk[par ^ 1] + (size_t)v * kBlk;
@@ -510,6 +571,7 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
         if (bs >= 0) blk[bs] = (double)val;
         if (us >= 0) upart[us] += (double)val;  // one owner lane per slot within the warp
       }
+     }
     }
   }
   __syncthreads();
