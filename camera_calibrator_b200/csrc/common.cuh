@@ -28,6 +28,11 @@ struct ccg_ctx {
   // multi-GPU
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
+  // peer-memory mailboxes for the fused reduce + allreduce + decide/solve kernels (ctx.cu)
+  void* mbox = nullptr;             // this rank's mailbox (cudaMalloc, exported through CUDA IPC)
+  void* mbox_peer[16] = {nullptr};  // every rank's mailbox mapped into this process ([rank] == mbox)
+  unsigned long long* d_seq = nullptr;  // device counter of completed peer allreduces
+  bool peer_ok = false;
   // pinned scratch for small D2H polls
   int* h_poll = nullptr;
   // event pool for opts.profile
@@ -48,6 +53,29 @@ int set_error(ccg_ctx* ctx, int status, const char* what, cudaError_t e = cudaSu
   } while (0)
 
 int nccl_allreduce_sum(ccg_ctx* ctx, double* buf, size_t count);
+
+// --------------------------------------------------------------------------
+// Allreduce of 64 doubles over peer memory (NVLink / NVSwitch), fused into the kernel that needs
+// the sum.  Every rank owns a mailbox with one slot per source rank and parity; a rank publishes
+// its 64 values into the slot (parity, own rank) of EVERY mailbox with plain peer stores, fences,
+// raises the slot's sequence number, then spins on the sequence numbers of its own mailbox and
+// sums the slots in rank order - so all ranks obtain bit-identical sums and the LM state machines
+// stay in lock step without a broadcast.  Two parities suffice: a rank can start allreduce k+2
+// only after every peer published k+1, i.e. after it finished reading k.
+// --------------------------------------------------------------------------
+constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerVals = 64;
+struct PeerSlot {
+  double data[kPeerVals];
+  unsigned long long seq;
+  unsigned long long pad[7];
+};
+struct PeerComm {
+  PeerSlot* box[kPeerMaxWorld];  // box[p] = rank p's mailbox: PeerSlot[2][kPeerMaxWorld]
+  unsigned long long* seq;       // this rank's counter of completed allreduces
+  int rank, world;
+};
+PeerComm peer_comm(const ccg_ctx* ctx);
 
 // device memory from the context's pool, ordered on ctx->stream
 cudaError_t pool_alloc(ccg_ctx* ctx, void** out, size_t bytes);
@@ -236,6 +264,53 @@ __device__ inline bool lm_decide(LmState& s, const LmParams& P, double cost_c, d
   }
   if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, n_done, true);
   return accept;
+}
+
+// Called by all threads of a CTA with at least kPeerVals threads; s_vals[0..64) in shared memory is
+// replaced by the sum over ranks.  A peer that does not show up within ~30 s poisons the sum with
+// NaN (the LM state machine then stops with CCG_ERR_NOT_FINITE) instead of hanging the GPU.
+__device__ inline void peer_allreduce64(double* s_vals, const PeerComm& pc) {
+  __shared__ unsigned long long s_seq;
+  __shared__ int s_timeout;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_seq = *pc.seq + 1ull;
+    s_timeout = 0;
+  }
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int par = (int)(seq & 1ull);
+  if (tid < kPeerVals) {
+    const double val = s_vals[tid];
+    for (int p = 0; p < pc.world; ++p) pc.box[p][par * kPeerMaxWorld + pc.rank].data[tid] = val;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (tid < pc.world) {
+    // release: the data stores of the whole CTA are ordered before the flag by the fence + barrier
+    unsigned long long* flag = &pc.box[tid][par * kPeerMaxWorld + pc.rank].seq;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    // acquire: wait for source rank `tid` in my own mailbox
+    const unsigned long long* mine = &pc.box[pc.rank][par * kPeerMaxWorld + tid].seq;
+    const long long t0 = clock64();
+    unsigned long long got = 0ull;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
+      if (got == seq) break;
+      if (clock64() - t0 > 60000000000ll) {
+        s_timeout = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < kPeerVals) {
+    double acc = 0.0;
+    for (int src = 0; src < pc.world; ++src) acc += __ldcg(&pc.box[pc.rank][par * kPeerMaxWorld + src].data[tid]);
+    s_vals[tid] = s_timeout ? nan("") : acc;
+  }
+  __syncthreads();
+  if (tid == 0) *pc.seq = seq;
 }
 
 // --------------------------------------------------------------------------

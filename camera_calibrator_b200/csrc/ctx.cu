@@ -3,7 +3,9 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -31,6 +33,7 @@ struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -53,6 +56,7 @@ static bool load_nccl() {
   g_nccl.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) return false;
@@ -78,6 +82,65 @@ void pool_free(ccg_ctx* ctx, void* ptr) {
   if (!ptr) return;
   if (!ctx->pool) cudaFree(ptr);
   else cudaFreeAsync(ptr, ctx->stream);
+}
+
+// ------------------------------------------------------- peer mailboxes ----
+PeerComm peer_comm(const ccg_ctx* ctx) {
+  PeerComm pc;
+  for (int p = 0; p < kPeerMaxWorld; ++p) pc.box[p] = (PeerSlot*)ctx->mbox_peer[p];
+  pc.seq = ctx->d_seq;
+  pc.rank = ctx->rank;
+  pc.world = ctx->world;
+  return pc;
+}
+
+// Exchange CUDA IPC handles of the mailboxes over the NCCL communicator and map every peer's
+// mailbox.  Failure is not an error: the partitioned solves then use ncclAllReduce.
+static void setup_peer_mailboxes(ccg_ctx* ctx) {
+  ctx->peer_ok = false;
+  if (getenv("CCG_NO_PEER") || ctx->world > kPeerMaxWorld || !g_nccl.AllGather) return;
+  const size_t bytes = sizeof(PeerSlot) * 2 * kPeerMaxWorld;
+  unsigned char* d_h = nullptr;
+  auto fail = [&]() {
+    cudaGetLastError();
+    if (d_h) cudaFree(d_h);
+  };
+  if (cudaMalloc(&ctx->mbox, bytes) != cudaSuccess || cudaMemset(ctx->mbox, 0, bytes) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->d_seq, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(ctx->d_seq, 0, sizeof(unsigned long long)) != cudaSuccess)
+    return fail();
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, ctx->mbox) != cudaSuccess) return fail();
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  if (cudaMalloc((void**)&d_h, hb * ctx->world) != cudaSuccess) return fail();
+  if (cudaMemcpy(d_h + hb * ctx->rank, &mine, hb, cudaMemcpyHostToDevice) != cudaSuccess) return fail();
+  // ncclUint8 = 1 (stable enum value of nccl.h)
+  if (g_nccl.AllGather(d_h + hb * ctx->rank, d_h, hb, 1, (ncclComm_t)ctx->nccl_comm, ctx->stream) != 0) return fail();
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail();
+  std::vector<cudaIpcMemHandle_t> all((size_t)ctx->world);
+  if (cudaMemcpy(all.data(), d_h, hb * ctx->world, cudaMemcpyDeviceToHost) != cudaSuccess) return fail();
+  int ok = 1;
+  for (int p = 0; p < ctx->world; ++p) {
+    if (p == ctx->rank) {
+      ctx->mbox_peer[p] = ctx->mbox;
+    } else if (cudaIpcOpenMemHandle(&ctx->mbox_peer[p], all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->mbox_peer[p] = nullptr;
+      ok = 0;
+    }
+  }
+  cudaFree(d_h);
+  d_h = nullptr;
+  // everyone must have mapped everyone before the first store: agree on the outcome
+  double* d_ok = nullptr;
+  if (cudaMalloc((void**)&d_ok, sizeof(double)) != cudaSuccess) return fail();
+  const double mine_ok = ok ? 0.0 : 1.0;
+  cudaMemcpy(d_ok, &mine_ok, sizeof(double), cudaMemcpyHostToDevice);
+  double bad = 1.0;
+  if (nccl_allreduce_sum(ctx, d_ok, 1) == CCG_OK && cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+    cudaMemcpy(&bad, d_ok, sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_ok);
+  ctx->peer_ok = bad == 0.0;
 }
 
 // ------------------------------------------------------------ profiler ----
@@ -222,6 +285,10 @@ int ccg_init(int device, ccg_ctx** out) {
 void ccg_destroy(ccg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (int p = 0; p < kPeerMaxWorld; ++p)
+    if (ctx->mbox_peer[p] && ctx->mbox_peer[p] != ctx->mbox) cudaIpcCloseMemHandle(ctx->mbox_peer[p]);
+  if (ctx->mbox) cudaFree(ctx->mbox);
+  if (ctx->d_seq) cudaFree(ctx->d_seq);
   if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
@@ -270,6 +337,7 @@ int ccg_comm_init(ccg_ctx* ctx, int rank, int world_size, const uint8_t id[128])
   const int rc = g_nccl.CommInitRank(&comm, world_size, uid, rank);
   if (rc != 0) return set_error(ctx, CCG_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitRank");
   ctx->nccl_comm = comm;
+  setup_peer_mailboxes(ctx);
   return CCG_OK;
 }
 

@@ -582,8 +582,8 @@ __device__ inline void decide_body(IntrState& ps, const LmParams& P, bool evalua
 
 // accept / reject after a sweep.  REDUCE: sum the partials here (single GPU);
 // otherwise read the (all-reduced) red_sweep buffer.
-template <bool REDUCE>
-__global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_decide(IntrDev d, LmParams P) {
+template <int REDUCE>
+__global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_decide(IntrDev d, LmParams P, PeerComm pc) {
   __shared__ double s_buf[kRedSeg * kSweepPart];
   IntrState& ps = d.ps[blockIdx.x];
   if (ps.lm.status != 0) return;
@@ -591,6 +591,8 @@ __global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_decide(IntrDev d,
   if (evaluated) {
     if (REDUCE) {
       block_reduce_items<kSweepPart>(d.sweep_part, ps.item0, ps.item1, s_buf);
+      // partitioned problem: every rank holds the same LM state, so all of them are here
+      if (REDUCE == 2) peer_allreduce64(s_buf, pc);
     } else {
       if (threadIdx.x < kSweepPart) s_buf[threadIdx.x] = d.red_sweep[(size_t)blockIdx.x * kSweepPart + threadIdx.x];
       __syncthreads();
@@ -659,13 +661,14 @@ __device__ inline void solve_body(IntrState& ps, const LmParams& P, const double
 }
 
 // reduced 9x9 solve.  Also evaluates the gradient norm at the current point.
-template <bool REDUCE>
-__global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, LmParams P) {
+template <int REDUCE>
+__global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, LmParams P, PeerComm pc) {
   __shared__ double s_buf[kRedSeg * kSchurPart];
   IntrState& ps = d.ps[blockIdx.x];
   if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
   if (REDUCE) {
     block_reduce_items<kSchurPart>(d.schur_part, ps.item0 * d.schur_split, ps.item1 * d.schur_split, s_buf);
+    if (REDUCE == 2) peer_allreduce64(s_buf, pc);
   } else {
     if (threadIdx.x < kSchurPart) s_buf[threadIdx.x] = d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x];
     __syncthreads();
@@ -893,10 +896,11 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   CCG_TRY(dev_alloc(p, &d.blk[1], (size_t)n_views * kBlk));
   CCG_TRY(dev_alloc(p, &d.yz, (size_t)n_views * kYz));
   CCG_TRY(dev_alloc(p, &d.sweep_part, items.size() * kSweepPart));
-  // elimination: 64 views per CTA pass; enough CTAs per item to fill the machine ~8x over
+  // elimination and candidate-pose kernels: 64 views per CTA pass, one pass per CTA (a partition of a
+  // large problem over 8 GPUs leaves ~85 views per item: two half-empty passes would double its latency)
   int64_t max_item_views = 1;
   for (const WorkItem& w : items) max_item_views = std::max<int64_t>(max_item_views, w.v1 - w.v0);
-  const int schur_split = (int)std::max<int64_t>(1, std::min<int64_t>((max_item_views + 127) / 128, 16));
+  const int schur_split = (int)std::max<int64_t>(1, std::min<int64_t>((max_item_views + 63) / 64, 32));
   CCG_TRY(dev_alloc(p, &d.schur_part, items.size() * (size_t)schur_split * kSchurPart));
   CCG_TRY(dev_alloc(p, &d.rt, (size_t)n_views * 12));
   CCG_TRY(dev_alloc(p, &d.step_part, items.size() * (size_t)schur_split * 2));
@@ -1011,17 +1015,23 @@ int launch_sweep_decide(ccg_intr_problem* p, const LmParams& P, Profiler& prof, 
   launch_sweep(p, P, res_out);
   prof.end();
   prof.begin(TAG_SMALL);
-  if (p->shared && ctx->world > 1) {
+  const PeerComm pc = peer_comm(ctx);
+  if (p->shared && ctx->world > 1 && ctx->peer_ok) {
+    // reduce + allreduce over peer memory + accept/reject in ONE kernel
+    k_intr_decide<2><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P, pc);
+    (*n_allreduce)++;
+    ctx->launches++;
+  } else if (p->shared && ctx->world > 1) {
     k_intr_reduce_sweep<<<nb, kRedSeg * kSweepPart, 0, st>>>(d);
     CCG_TRY(nccl_allreduce_sum(ctx, d.red_sweep, (size_t)nb * kSweepPart));
     (*n_allreduce)++;
-    k_intr_decide<false><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P);
+    k_intr_decide<0><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P, pc);
     ctx->launches += 2;
   } else if (p->single_item) {
     k_intr_decide_batch<<<(nb + kBatchThreads - 1) / kBatchThreads, kBatchThreads, 0, st>>>(d, P, nb);
     ctx->launches++;
   } else {
-    k_intr_decide<true><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P);
+    k_intr_decide<1><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P, pc);
     ctx->launches++;
   }
   prof.end();
@@ -1038,17 +1048,22 @@ int launch_schur_solve(ccg_intr_problem* p, const LmParams& P, Profiler& prof, i
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
-  if (p->shared && ctx->world > 1) {
+  const PeerComm pc = peer_comm(ctx);
+  if (p->shared && ctx->world > 1 && ctx->peer_ok) {
+    k_intr_solve<2><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P, pc);
+    (*n_allreduce)++;
+    ctx->launches++;
+  } else if (p->shared && ctx->world > 1) {
     k_intr_reduce_schur<<<nb, kRedSeg * kSchurPart, 0, st>>>(d);
     CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, (size_t)nb * kSchurPart));
     (*n_allreduce)++;
-    k_intr_solve<false><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P);
+    k_intr_solve<0><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P, pc);
     ctx->launches += 2;
   } else if (p->single_item) {
     k_intr_solve_batch<<<(nb + kBatchThreads - 1) / kBatchThreads, kBatchThreads, 0, st>>>(d, P, nb);
     ctx->launches++;
   } else {
-    k_intr_solve<true><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P);
+    k_intr_solve<1><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P, pc);
     ctx->launches++;
   }
   prof.end();
@@ -1084,6 +1099,12 @@ int run_problem(ccg_intr_problem* p, const ccg_opts& opts, ccg_timing* timing) {
   }
   cudaEventRecord(ctx->events[ev_total0], ctx->stream);
   CCG_TRY(reset_problem(p, P));  // restoring the initial parameters is part of the timed solve
+  if (p->shared && ctx->world > 1 && ctx->peer_ok) {
+    // line the ranks up once per solve with a collective that waits without a deadline; the
+    // peer-memory allreduces inside the kernels then only see the skew of one LM iteration
+    CCG_TRY(nccl_allreduce_sum(ctx, p->dev.red_sweep, 1));
+    n_allreduce++;
+  }
   CCG_TRY(launch_sweep_decide(p, P, prof, nullptr, &n_allreduce));
   // per-kernel events stay outside graphs; the NCCL allreduces of a partitioned problem are captured
   // with the kernels (CCG_NO_GRAPH=1 disables graphs altogether)
