@@ -6,17 +6,19 @@
 //       reference src/calibrator.cpp:183-219 (model :70-95, layout :168-179)
 //   the Ceres problem build and ceres::Solve call
 //       reference src/calibrator.cpp:236-324
-// Design (DESIGN.md "Single-camera kernels"):
-//   * observations live in HBM as SoA float32 (u,v,X,Y,Z: 20 B/obs), read with
-//     coalesced 128-byte warp loads; pose and intrinsics are staged per view
-//   * a warp PAIR owns a view: both warps sweep all of its observations, warp A
-//     accumulates V(21) g_v(6) W[:,fx fy px py](24) + cost, warp B accumulates
-//     W[:,k1 k2 p1 p2 k3](30) + U(35) + g_u(9).  Lane-private FP64 accumulators,
-//     one transposing shuffle reduction per view (31 shuffles per 32 values)
-//   * the 9x9 reduced system is summed from per-CTA partials in a fixed order,
-//     so results are bit-reproducible for a given launch geometry
-//   * accept/reject, trust-region update and termination run on the device;
-//     the host only enqueues kernels and polls one counter
+// Design:
+//   * observations live in HBM as SoA float32 (u,v,X,Y,Z: 20 B/obs); per-view pose and blocks in FP64
+//   * three sweep variants behind ccg_opts.hessian_fp64, all with FP64 residual, cost and gradient:
+//       0 (default) k_intr_sweep_tc, intr_tc.cuh: warp-specialised, J'J on the TF32 tensor cores
+//       1           k_intr_sweep below: everything FP64, a warp PAIR per view (warp A accumulates
+//                   V(21) g_v(6) W[:,fx fy px py](24) + cost, warp B W[:,k1 k2 p1 p2 k3](30) + U(35) +
+//                   g_u(9); lane-private accumulators, one transposing shuffle reduction per view)
+//       2           k_intr_sweep_mixed, intr_mixed.cuh: J'J with FP32 FFMAs
+//   * the 9x9 reduced system is summed from per-CTA partials in a fixed order, so results are
+//     bit-reproducible for a given launch geometry (and bit-identical on every rank of a partition)
+//   * accept/reject, trust-region update and termination run on the device; the host replays one LM
+//     iteration as a CUDA graph and polls one counter
+//   * Calibrator::Estimate's closed-form initialisation runs on the device too (intr_init.cuh)
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
