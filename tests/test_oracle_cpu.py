@@ -213,3 +213,51 @@ def test_rig_oracle_huber_and_costs():
     assert np.any(cost > 0.5 * a * a)
     assert np.array_equal(qc[0], s.q_c[0]) and np.array_equal(tc[0], s.t_c[0])  # frozen camera
     assert np.max(np.abs(tc - s.t_c_true)) < 5e-3
+
+
+def test_rig_oracle_matches_scipy_block_huber():
+    """Independent pin of the rig oracle (the reference has no assertion on this path): scipy
+    least_squares on the robustified residuals r * sqrt(rho(s) / s), s = ||r||^2 per 2-vector block
+    - Huber per OBSERVATION as Ceres applies it (extrinsics_calibrator.cpp:175-176), not per scalar
+    like scipy's own loss='huber' - must reach the oracle's cost and camera extrinsics."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+
+    from camera_calibrator_b200 import synth
+
+    C, F = 2, 12
+    s = synth.rig_scene(n_cams=C, n_frames=F, grid=(4, 3), seed=11, outlier_fraction=0.08)
+    qc, tc, qf, tf, cost, rep = oracle.rig_solve(s.u, s.v, s.obs_cam, s.obs_point, s.frame_offsets, s.Xw, s.q_c,
+                                                 s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    assert rep["termination"] in (1, 2, 3)
+    a = float(np.float32(3.0) / np.float32(500.0))
+    frame_of_obs = np.repeat(np.arange(F), np.diff(s.frame_offsets))
+    Xw = s.Xw.astype(np.float64)[s.obs_point]
+    uv = np.stack([s.u, s.v], 1).astype(np.float64)
+    cam = s.obs_cam.astype(np.int64)
+    Rc0, Rf0 = quat_to_rot(s.q_c), quat_to_rot(s.q_f)
+
+    def unpack(p):
+        # camera 0 is frozen; cameras 1.. and all frames: rotation-vector increment (left) + translation
+        dc = p[:6 * (C - 1)].reshape(C - 1, 6)
+        df = p[6 * (C - 1):].reshape(F, 6)
+        Rc = np.concatenate([Rc0[:1], np.einsum("cij,cjk->cik", Rotation.from_rotvec(dc[:, :3]).as_matrix(), Rc0[1:])])
+        tcam = np.concatenate([s.t_c[:1], s.t_c[1:] + dc[:, 3:]])
+        Rf = np.einsum("fij,fjk->fik", Rotation.from_rotvec(df[:, :3]).as_matrix(), Rf0)
+        return Rc, tcam, Rf, s.t_f + df[:, 3:]
+
+    def robust(p):
+        Rc, tcam, Rf, tfr = unpack(p)
+        x_rig = np.einsum("nij,nj->ni", Rf[frame_of_obs], Xw) + tfr[frame_of_obs]
+        x = np.einsum("nij,nj->ni", Rc[cam], x_rig) + tcam[cam]
+        r = np.stack([x[:, 0] / x[:, 2], x[:, 1] / x[:, 2]], 1) - uv
+        sq = np.maximum(np.sum(r * r, 1), 1e-300)
+        rho = np.where(sq <= a * a, sq, 2 * a * np.sqrt(sq) - a * a)
+        return (r * np.sqrt(rho / sq)[:, None]).ravel()
+
+    sol = least_squares(robust, np.zeros(6 * (C - 1) + 6 * F), method="trf", x_scale="jac", xtol=1e-15, ftol=1e-15,
+                        gtol=1e-14, max_nfev=400)
+    assert abs(0.5 * np.sum(sol.fun**2) - rep["final_cost"]) <= 1e-7 * rep["final_cost"]
+    Rc, tcam, _, _ = unpack(sol.x)
+    assert np.max(np.abs(tcam - tc)) <= 2e-6
+    assert np.max(np.abs(Rc - quat_to_rot(qc))) <= 2e-6
