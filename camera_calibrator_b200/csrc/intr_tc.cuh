@@ -34,7 +34,10 @@ constexpr int kTcJ = kTcWarps - kTcD;  // Jacobian/tensor-role warps
 constexpr int kTcRow = 20;         // floats per Jacobian row in the tile (16 + 4: conflict-free STS.128 and LDS.64)
 constexpr int kTcTile = 64 * kTcRow;  // one 32-observation tile; every warp owns two (double buffer)
 constexpr int kTcSlots = 256;         // observations the circular staging buffer of a warp holds (8 granules of 32)
-constexpr int kTcAhead = 2;           // granules requested beyond the one being consumed
+#ifndef CCG_TC_AHEAD
+#define CCG_TC_AHEAD 2
+#endif
+constexpr int kTcAhead = CCG_TC_AHEAD;  // granules requested beyond the one being consumed (ring holds 8)
 constexpr int kTcBatch = 16;          // views whose poses and offsets a warp stages at a time
 // floats per warp: u v X Y Z circular buffers | 16 poses (12 doubles each) | 17 view offsets (int)
 constexpr int kTcRing = 5 * kTcSlots + kTcBatch * 24 + 32;
