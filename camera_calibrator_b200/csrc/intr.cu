@@ -749,16 +749,19 @@ __global__ void k_intr_init_state(IntrDev d, LmParams P, const double* intr0, co
 __global__ void __launch_bounds__(128) k_intr_gather(IntrDev d, const int64_t* __restrict__ problem_off, int n_problems,
                                                     double* __restrict__ q, double* __restrict__ t,
                                                     double* __restrict__ intr, ccg_report* __restrict__ rep) {
-  const int b = blockIdx.x;
+  // grid: (view blocks of the largest problem, problems)
+  const int b = blockIdx.y;
   const IntrState& ps = d.ps[b];
   const int par = ps.lm.par;
   const double* pose = d.pose[par];
-  for (int64_t v = problem_off[b] + threadIdx.x; v < problem_off[b + 1]; v += blockDim.x) {
+  const int64_t v = problem_off[b] + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < problem_off[b + 1]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) q[v * 4 + k] = pose[v * kPose + k];
 #pragma unroll
     for (int k = 0; k < 3; ++k) t[v * 3 + k] = pose[v * kPose + 4 + k];
   }
+  if (blockIdx.x != 0) return;
   if (threadIdx.x < 9) intr[(size_t)b * 9 + threadIdx.x] = ps.intr[par][threadIdx.x];
   if (threadIdx.x == 0) {
     ccg_report r;
@@ -1181,7 +1184,12 @@ int download_problem(ccg_intr_problem* p, double* intr, double* q, double* t, cc
     CCG_TRY(dev_alloc(p, &p->d_out_intr, (size_t)nb * 9));
     CCG_TRY(dev_alloc(p, &p->d_out_rep, (size_t)nb));
   }
-  k_intr_gather<<<(int)nb, 128, 0, st>>>(p->dev, p->d_problem_off, (int)nb, p->d_out_q, p->d_out_t, p->d_out_intr, p->d_out_rep);
+  int64_t max_views = 1;
+  for (int64_t b = 0; b < nb; ++b)
+    max_views = std::max(max_views, p->problem_off[(size_t)b + 1] - p->problem_off[(size_t)b]);
+  if (nb > 65535) return set_error(ctx, CCG_ERR_UNSUPPORTED, "more than 65535 problems in one batch");
+  k_intr_gather<<<dim3((unsigned)((max_views + 127) / 128), (unsigned)nb), 128, 0, st>>>(
+      p->dev, p->d_problem_off, (int)nb, p->d_out_q, p->d_out_t, p->d_out_intr, p->d_out_rep);
   ctx->launches++;
   std::vector<ccg_report> rep_local;
   if (!reports) {
@@ -1350,6 +1358,7 @@ int ccg_intrinsics_estimate_batch(ccg_ctx* ctx, const float* u, const float* v, 
                                   double* intr, double* q, double* t, double* intr_init,
                                   uint32_t const_intr_mask, const ccg_opts* opts, ccg_report* reports) {
   if (!ctx || !intr || n_problems < 1 || n_views < 0) return CCG_ERR_BAD_ARG;
+  if (n_problems > 65535) return set_error(ctx, CCG_ERR_UNSUPPORTED, "more than 65535 problems in one batch");
   const int64_t one[2] = {0, n_views};
   if (!problem_offsets) {
     if (n_problems != 1) return set_error(ctx, CCG_ERR_BAD_ARG, "problem_offsets required");
