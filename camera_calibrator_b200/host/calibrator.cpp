@@ -42,12 +42,6 @@ enum { OFF_FX = 0, OFF_FY, OFF_PX, OFF_PY, OFF_K1, OFF_K2, OFF_P1, OFF_P2, OFF_K
 
 Calibrator::Calibrator(const int img_width, const int img_height) : width_(img_width), height_(img_height) {}
 
-void Calibrator::EstimateOpenCv(const std::vector<Points2D>&, const std::vector<Points3D>&) {
-  throw std::runtime_error(
-      "Calibrator::EstimateOpenCv delegates to cv::calibrateCamera in the reference; OpenCV C++ is not part "
-      "of this build (out of scope). Use Estimate().");
-}
-
 namespace {
 SolveReport ToReport(const ccg_report& rep) {
   SolveReport r;
@@ -136,6 +130,33 @@ void Calibrator::Estimate(const std::vector<Points2D>& in_img_points,
                                          (int64_t)n_img, intr, q.data(), t.data(), init, mask, &opts, &rep);
   if (rc != CCG_OK)
     throw std::runtime_error(std::string("Calibrator::Estimate: ") + ccg_status_string(rc) + " " +
+                             ccg_last_error(ctx));
+  StoreResult(ToReport(rep), intr, q.data(), t.data(), n_img);
+}
+
+void Calibrator::EstimateOpenCv(const std::vector<Points2D>& in_img_points,
+                                const std::vector<Points3D>& in_world_points) {
+  // The reference hands the points to cv::calibrateCamera with flags = 0 (calibrator.cpp:16-45): OpenCV
+  // ignores the current K_ / dist_ and the frozen set, initialises from the homographies itself and
+  // minimises the same reprojection error over fx fy cx cy k1 k2 p1 p2 k3 and one pose per view.  The
+  // minimum of that cost is what ccg_intrinsics_estimate converges to (the oracle is pinned against
+  // cv2.calibrateCamera: RMS to 1e-9, K to 1e-6), so the call runs the device path with nothing frozen.
+  if (in_img_points.size() != in_world_points.size())
+    throw std::invalid_argument("Calibrator::EstimateOpenCv: image/world view counts differ");
+  const size_t n_img = in_img_points.size();
+  std::vector<int64_t> off;
+  std::vector<float> u, v, X, Y, Z;
+  PackObservations(in_img_points, in_world_points, "Calibrator::EstimateOpenCv", &off, &u, &v, &X, &Y, &Z);
+  std::vector<double> q(4 * std::max<size_t>(n_img, 1)), t(3 * std::max<size_t>(n_img, 1));
+  double intr[NUM_INTR], init[NUM_INTR];
+  ccg_opts opts;
+  ccg_default_opts(&opts);
+  ccg_report rep;
+  ccg_ctx* ctx = HostContext();
+  const int rc = ccg_intrinsics_estimate(ctx, u.data(), v.data(), X.data(), Y.data(), Z.data(), off.data(),
+                                         (int64_t)n_img, intr, q.data(), t.data(), init, 0u, &opts, &rep);
+  if (rc != CCG_OK)
+    throw std::runtime_error(std::string("Calibrator::EstimateOpenCv: ") + ccg_status_string(rc) + " " +
                              ccg_last_error(ctx));
   StoreResult(ToReport(rep), intr, q.data(), t.data(), n_img);
 }

@@ -25,8 +25,9 @@ class Calibrator {
  public:
   Calibrator(const int img_width, const int img_height);
 
-  // reference: delegates to cv::calibrateCamera (calibrator.cpp:16-45).  OpenCV C++ is not
-  // part of this build; the call throws std::runtime_error (out of scope).
+  // reference: delegates to cv::calibrateCamera with flags = 0 (calibrator.cpp:16-45), i.e. own
+  // initialisation, nothing frozen, same reprojection cost.  Here: the device Estimate path with an
+  // empty frozen set (same minimum; OpenCV itself is not linked).
   void EstimateOpenCv(const std::vector<Points2D>& in_img_points, const std::vector<Points3D>& in_world_points);
 
   // closed-form initialisation (homographies -> K -> per-view pose) then Optimize (calibrator.cpp:47-68);

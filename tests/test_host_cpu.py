@@ -67,7 +67,7 @@ def test_calibrator_accessors(pc):
     c.SetDistortion(distortion=dist)
     assert np.array_equal(c.GetK(), K) and np.array_equal(c.GetDistortion(), dist)
     with pytest.raises(RuntimeError):
-        c.EstimateOpenCv([], [])
+        c.EstimateOpenCv([], [])  # no views (and, on a box without a GPU, no device)
     import torch
 
     if not torch.cuda.is_available():

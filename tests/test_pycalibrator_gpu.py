@@ -148,3 +148,22 @@ def test_calibrator_lens_round_trip(pc):
     assert np.max(np.abs(back - norm)) < 2e-6  # float32 pixels in, float32 out
     # lists of rows work like the reference's stl+eigen casters
     assert np.allclose(c.Distort([[0.1, 0.2], [0.0, 0.0]])[1], [800, 500])
+
+
+def test_estimate_opencv_matches_cv2_calibrate_camera(pc):
+    """EstimateOpenCv (calibrator.cpp:16-45) against the function the reference calls there."""
+    import cv2
+
+    d = oracle.datagen_planar(12, 80, seed=4)
+    img, world = _views(d)
+    crit = (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER, 2000, 1e-16)
+    rms, K, dist, _, _ = cv2.calibrateCamera([w.astype(np.float32) for w in world], [i.astype(np.float32) for i in img],
+                                             (1600, 1000), None, None, criteria=crit)
+    c = pc.Calibrator(1600, 1000)
+    c.ForceDistortionToConstant(4)  # ignored by this entry point, as cv::calibrateCamera ignores it
+    c.EstimateOpenCv(img_points=img, world_points=world)
+    Kg, dg = c.GetK(), c.GetDistortion()
+    assert abs(c.GetLastReport()["rms"] - rms) <= 1e-8
+    for got, want in ((Kg[0, 0], K[0, 0]), (Kg[1, 1], K[1, 1]), (Kg[0, 2], K[0, 2]), (Kg[1, 2], K[1, 2])):
+        assert abs(got - want) / want <= 2e-6
+    assert np.max(np.abs(dg - dist.ravel()[:5])) <= 1e-5 and dg[4] != 0.0
