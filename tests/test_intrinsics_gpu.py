@@ -228,3 +228,24 @@ def test_lens_kernels_match_float64_model(ctx):
     fx = (x * mm + 2 * d[2] * x * y + d[3] * (r2 + 2 * x * x)) * float(K[0, 0]) + float(K[0, 2])
     fy = (y * mm + 2 * d[3] * x * y + d[2] * (r2 + 2 * y * y)) * float(K[1, 1]) + float(K[1, 2])
     assert np.max(np.abs(fx - pu)) < 3e-4 and np.max(np.abs(fy - pv)) < 3e-4  # float32 rounding of the output (6e-8 x 1e3 px) and of the pixels
+
+
+@pytest.mark.parametrize("name", ["reference_test_5x100", "c1_20x54"])
+def test_estimate_matches_cv2_golden(ctx, name):
+    """The committed golden vectors (tests/golden/intrinsics_golden.json): cv2.calibrateCamera - the
+    function the reference's EstimateOpenCv calls (calibrator.cpp:38), same cost - run to convergence
+    on the reference fixture's data.  The CUDA path, without the oracle's solver: 1e-6 on K, 2e-4 on
+    the distortion (cv2 stops on its own criterion), 1e-9 on the RMS."""
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "intrinsics_golden.json")))[name]
+    d = oracle.datagen_planar(g["n_views"], g["n_points"])  # the generator only (pinned by the same file)
+    for k in "uvXY":
+        assert float(np.sum(getattr(d, k).astype(np.float64))) == g["checksum"][k]
+    gi, _, _, rep, _ = ctx.intrinsics_estimate(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets)
+    cv = np.array(g["cv2"]["K"] + g["cv2"]["dist"])
+    assert rep["termination"] in (1, 2, 3)
+    assert np.max(np.abs(gi[:4] - cv[:4]) / cv[:4]) <= 1e-6
+    assert np.max(np.abs(gi[4:] - cv[4:]) / np.abs(cv[4:])) <= 2e-4
+    assert abs(rep["rms"] - g["cv2"]["rms"]) <= 1e-9

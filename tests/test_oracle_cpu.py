@@ -261,3 +261,27 @@ def test_rig_oracle_matches_scipy_block_huber():
     Rc, tcam, _, _ = unpack(sol.x)
     assert np.max(np.abs(tcam - tc)) <= 2e-6
     assert np.max(np.abs(Rc - quat_to_rot(qc))) <= 2e-6
+
+
+def _rig_golden():
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rig_golden.json")))
+    i = g["inputs"]
+    args = (np.array(i["u"], np.float32), np.array(i["v"], np.float32), np.array(i["obs_cam"], np.int32),
+            np.array(i["obs_point"], np.int64), np.array(i["frame_offsets"], np.int64), np.array(i["Xw"], np.float32),
+            np.array(i["q_c"]), np.array(i["t_c"]), np.array(i["cam_frozen"], np.uint8), np.array(i["q_f"]),
+            np.array(i["t_f"]))
+    return g, args
+
+
+def test_rig_oracle_matches_golden_fixture():
+    """Committed rig fixture (inputs + an independent scipy block-Huber solution, tests/golden/
+    make_golden.py): the oracle must reproduce cost, extrinsics and per-observation costs."""
+    g, args = _rig_golden()
+    qc, tc, qf, tf, cost, rep = oracle.rig_solve(*args)
+    sp = g["scipy"]
+    assert abs(rep["final_cost"] - sp["cost"]) <= 1e-7 * sp["cost"]
+    assert np.max(np.abs(tc - np.array(sp["t_c"]))) <= 2e-6
+    assert np.max(np.abs(quat_to_rot(qc) - np.array(sp["R_c"]))) <= 2e-6
+    assert np.max(np.abs(tf - np.array(sp["t_f"]))) <= 2e-5
+    assert np.allclose(cost, np.array(sp["obs_cost"]), rtol=1e-3, atol=1e-9)
+    assert abs(rep["final_cost"] - g["oracle"]["final_cost"]) <= 1e-12 * g["oracle"]["final_cost"]  # regression pin

@@ -86,3 +86,29 @@ def test_rig_too_many_cameras_is_reported(ctx):
     with pytest.raises(cc.CcgError) as e:
         rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
     assert e.value.status == -5
+
+
+def test_rig_gpu_matches_golden_fixture(ctx):
+    """The committed rig fixture, without the oracle: the CUDA path against the independent scipy
+    block-Huber solution stored in tests/golden/rig_golden.json (cost, camera and frame extrinsics,
+    per-observation costs in the caller's order)."""
+    import json
+    import os
+
+    from helpers import quat_to_rot
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rig_golden.json")))
+    i = g["inputs"]
+    got = rig_api.rig_solve(ctx, np.array(i["u"], np.float32), np.array(i["v"], np.float32),
+                            np.array(i["obs_cam"], np.int32), np.array(i["obs_point"], np.int64),
+                            np.array(i["frame_offsets"], np.int64), np.array(i["Xw"], np.float32), np.array(i["q_c"]),
+                            np.array(i["t_c"]), np.array(i["cam_frozen"], np.uint8), np.array(i["q_f"]), np.array(i["t_f"]))
+    qc, tc, qf, tf, cost, rep = got
+    sp = g["scipy"]
+    assert rep["termination"] in (1, 2, 3)
+    assert abs(rep["final_cost"] - sp["cost"]) <= 1e-7 * sp["cost"]
+    assert np.max(np.abs(tc - np.array(sp["t_c"]))) <= 2e-6
+    assert np.max(np.abs(quat_to_rot(qc) - np.array(sp["R_c"]))) <= 2e-6
+    assert np.max(np.abs(tf - np.array(sp["t_f"]))) <= 2e-5
+    assert np.allclose(cost, np.array(sp["obs_cost"]), rtol=1e-3, atol=1e-9)
+    assert np.array_equal(qc[0], np.array(i["q_c"])[0]) and np.array_equal(tc[0], np.array(i["t_c"])[0])  # frozen camera
