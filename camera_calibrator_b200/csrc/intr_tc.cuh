@@ -31,6 +31,11 @@ constexpr int kTcWarps = CCG_TC_WARPS;  // warps per CTA, one CTA per SM
 #endif
 constexpr int kTcD = CCG_TC_D;     // FP64-role warps (the first kTcD warps of the CTA)
 constexpr int kTcJ = kTcWarps - kTcD;  // Jacobian/tensor-role warps
+static_assert(kTcD == kTcJ, "a Jacobian warp shares its view range with one FP64 warp");
+#ifndef CCG_TC_TAIL
+#define CCG_TC_TAIL 10
+#endif
+constexpr int kTcTail = CCG_TC_TAIL;  // 64ths of a range's FP64 work done by the Jacobian warp afterwards
 constexpr int kTcRow = 20;         // floats per Jacobian row in the tile (16 + 4: conflict-free STS.128 and LDS.64)
 constexpr int kTcTile = 64 * kTcRow;  // one 32-observation tile; every warp owns two (double buffer)
 constexpr int kTcSlots = 256;         // observations the circular staging buffer of a warp holds (8 granules of 32)
@@ -414,50 +419,19 @@ __global__ void __launch_bounds__(kStepThreads) k_intr_step(IntrDev d) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// The sweep.  One CTA per work item; the first kTcD warps run the FP64 role, the others the
-// Jacobian role, so the FP64 pipe and the FP32 + tensor pipes of every SM sub-partition are fed
-// by different warps at the same time.  Each role walks ALL views of the item on its own
-// (view v goes to role-warp v mod role size: static, so sums are bit-reproducible); the roles
-// share nothing, so there is no synchronisation inside the loops, and the second reader of an
-// observation line hits L1/L2 (HBM traffic stays 20 B per observation).  The split 7 : 9 balances
-// the measured role times (FP64 role 0.78 of the Jacobian role per observation).
+// The FP64 role over the contiguous view range [vw0, vw1): residuals, cost, g_u (into the warp's
+// partial) and g_v (into the view blocks).
 // ---------------------------------------------------------------------------------------------
 template <bool RES>
-__global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, double* __restrict__ res_out) {
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  double(*s_part)[kSweepPart] = reinterpret_cast<double(*)[kSweepPart]>(s_dyn);
-  float* s_rings = reinterpret_cast<float*>(s_dyn + sizeof(double) * kTcWarps * kSweepPart);
-  float* s_tiles = s_rings + kTcWarps * kTcRing;
-  __shared__ double s_k[9];
-  __shared__ int s_meta[2];
-  const WorkItem it = d.items[blockIdx.x];
-  IntrState& ps = d.ps[it.problem];
-  if (threadIdx.x == 0) {
-    s_meta[0] = ps.lm.par;
-    s_meta[1] = (ps.lm.status == 0 && ps.lm.solve_ok) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_meta[1]) return;
-  const int par = s_meta[0];
-  if (threadIdx.x < 9) s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
-  for (int i = threadIdx.x; i < kTcWarps * kSweepPart; i += blockDim.x) (&s_part[0][0])[i] = 0.0;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool jac_role = warp >= kTcD;
-  float* ring = s_rings + warp * kTcRing;
-  double* upart = s_part[warp];
-
-  if (!jac_role) {
-    // =========================== FP64 role ===========================
+__device__ __forceinline__ void tc_run_fp64_role(const IntrDev& d, float* ring, const double* s_k, int par, int vw0,
+                                                 int vw1, int lane, double* upart, double* __restrict__ res_out) {
+  {
     TcConst64 K;
     K.fx = s_k[0]; K.fy = s_k[1]; K.cx = s_k[2]; K.cy = s_k[3];
     K.k1 = s_k[4]; K.k2 = s_k[5]; K.p1 = s_k[6]; K.p2 = s_k[7]; K.k3 = s_k[8];
     double gu[9], cost = 0.0;
 #pragma unroll
     for (int i = 0; i < 9; ++i) gu[i] = 0.0;
-    // this warp's contiguous share of the item's views
-    const int nvw = it.v1 - it.v0;
-    const int vw0 = it.v0 + (int)((int64_t)nvw * warp / kTcD), vw1 = it.v0 + (int)((int64_t)nvw * (warp + 1) / kTcD);
     const double* s_pose = reinterpret_cast<const double*>(ring + 5 * kTcSlots);
     const int* s_off = reinterpret_cast<const int*>(ring + 5 * kTcSlots + kTcBatch * 24);
     TcStream<5> strm(d, ring, d.view_off[vw0], d.view_off[vw1], lane);
@@ -510,6 +484,52 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
     r += __shfl_xor_sync(0xffffffffu, r, 16);
     if (lane < 9) upart[16 + lane] = r;
     else if (lane == 9) upart[0] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The sweep.  One CTA per work item; the first kTcD warps run the FP64 role, the others the
+// Jacobian role, so the FP64 pipe and the FP32 + tensor pipes of every SM sub-partition are fed
+// by different warps at the same time.  Each role walks ALL views of the item on its own
+// (view v goes to role-warp v mod role size: static, so sums are bit-reproducible); the roles
+// share nothing, so there is no synchronisation inside the loops, and the second reader of an
+// observation line hits L1/L2 (HBM traffic stays 20 B per observation).  The split 7 : 9 balances
+// the measured role times (FP64 role 0.78 of the Jacobian role per observation).
+// ---------------------------------------------------------------------------------------------
+template <bool RES>
+__global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, double* __restrict__ res_out) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double(*s_part)[kSweepPart] = reinterpret_cast<double(*)[kSweepPart]>(s_dyn);
+  float* s_rings = reinterpret_cast<float*>(s_dyn + sizeof(double) * kTcWarps * kSweepPart);
+  float* s_tiles = s_rings + kTcWarps * kTcRing;
+  __shared__ double s_k[9];
+  __shared__ int s_meta[2];
+  const WorkItem it = d.items[blockIdx.x];
+  IntrState& ps = d.ps[it.problem];
+  if (threadIdx.x == 0) {
+    s_meta[0] = ps.lm.par;
+    s_meta[1] = (ps.lm.status == 0 && ps.lm.solve_ok) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_meta[1]) return;
+  const int par = s_meta[0];
+  if (threadIdx.x < 9) s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
+  for (int i = threadIdx.x; i < kTcWarps * kSweepPart; i += blockDim.x) (&s_part[0][0])[i] = 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool jac_role = warp >= kTcD;
+  float* ring = s_rings + warp * kTcRing;
+  double* upart = s_part[warp];
+
+  // The FP64 role is the slower one when both run (the Jacobian warps used to wait ~12 % of the
+  // kernel at the final barrier), so a Jacobian warp also takes the last kTcTail / 64 of its partner's
+  // FP64 work once its own range is done.  The split is static: sums stay bit-reproducible.
+  const int nvw_item = it.v1 - it.v0, rw = jac_role ? warp - kTcD : warp;
+  const int vw0 = it.v0 + (int)((int64_t)nvw_item * rw / kTcD), vw1 = it.v0 + (int)((int64_t)nvw_item * (rw + 1) / kTcD);
+  const int vsplit = vw0 + ((vw1 - vw0) * (64 - kTcTail) + 32) / 64;
+  if (!jac_role) {
+    // =========================== FP64 role ===========================
+    tc_run_fp64_role<RES>(d, ring, s_k, par, vw0, vsplit, lane, upart, res_out);
   } else {
     // =========================== Jacobian + tensor role ===========================
     const int g = lane >> 2, tig = lane & 3;
@@ -517,8 +537,6 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
     TcConst32 K;
     K.fx = (float)s_k[0]; K.fy = (float)s_k[1];
     K.k1 = (float)s_k[4]; K.k2 = (float)s_k[5]; K.p1 = (float)s_k[6]; K.p2 = (float)s_k[7]; K.k3 = (float)s_k[8];
-    const int jw = warp - kTcD, nvw = it.v1 - it.v0;
-    const int vw0 = it.v0 + (int)((int64_t)nvw * jw / kTcJ), vw1 = it.v0 + (int)((int64_t)nvw * (jw + 1) / kTcJ);
     const double* s_pose = reinterpret_cast<const double*>(ring + 5 * kTcSlots);
     const int* s_off = reinterpret_cast<const int*>(ring + 5 * kTcSlots + kTcBatch * 24);
     TcStream<3> strm(d, ring, d.view_off[vw0], d.view_off[vw1], lane);
@@ -576,6 +594,10 @@ __global__ void __launch_bounds__(kTcWarps * 32, 1) k_intr_sweep_tc(IntrDev d, d
       }
      }
     }
+    // the tail of the partner's FP64 work (the ring is free again: every granule has been consumed)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    tc_run_fp64_role<RES>(d, ring, s_k, par, vsplit, vw1, lane, upart, res_out);
   }
   __syncthreads();
   if (threadIdx.x < kSweepPart) {
