@@ -11,7 +11,8 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libccg.so")
+# CCG_LIB selects an experimental build of the library (tools/build_variant.sh); default: the in-tree libccg.so
+LIB_PATH = os.environ.get("CCG_LIB") or os.path.join(_PKG, "libccg.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 

@@ -173,8 +173,8 @@ class Context:
         return intr, q, t, [r.asdict() for r in reps], init
 
     def intrinsics_eval(self, u, v, X, Y, Z, view_offsets, intr, q, t, hessian_fp64=0):
-        """One sweep at the given point.  hessian_fp64: 0 tensor-core TF32 J'J (default sweep), 1 all FP64,
-        2 FP32 FFMA J'J (ccg_opts.hessian_fp64)."""
+        """One sweep at the given point.  hessian_fp64: 0 tensor-core TF32 J'J (default sweep), 1 all FP64
+        (ccg_opts.hessian_fp64)."""
         u, v, X, Y, Z = map(f32, (u, v, X, Y, Z))
         off = i64(view_offsets)
         nv = len(off) - 1

@@ -40,6 +40,8 @@ struct ccg_ctx {
   // stream-ordered device memory pool: freed problem buffers stay cached for the next solve
   // (cudaMalloc/cudaFree of the ~1 GB of a large calibration cost more than its whole LM loop)
   cudaMemPool_t pool = nullptr;
+  // per-device opt-in of the default sweep's dynamic shared memory ([RES variant])
+  bool sweep_attr[2] = {false, false};
 };
 
 namespace ccg {
@@ -326,6 +328,23 @@ __device__ __forceinline__ double warp_reduce32(double (&a)[32], int lane) {
     for (int i = 0; i < half; ++i) {
       const double send = up ? a[i] : a[i + half];
       const double keep = up ? a[i + half] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return a[0];
+}
+
+// transposing reduction over a group of G lanes (G = 8, 16, 32): a[0..G) per lane in, the sum over
+// the group's lanes of a[gl] out (gl = lane within the group)
+template <int G, typename T>
+__device__ __forceinline__ T group_reduce(T (&a)[G], int gl) {
+#pragma unroll
+  for (int half = G / 2; half >= 1; half >>= 1) {
+    const bool up = (gl & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const T send = up ? a[i] : a[i + half];
+      const T keep = up ? a[i + half] : a[i];
       a[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
     }
   }

@@ -8,12 +8,12 @@
 //       reference src/calibrator.cpp:236-324
 // Design:
 //   * observations live in HBM as SoA float32 (u,v,X,Y,Z: 20 B/obs); per-view pose and blocks in FP64
-//   * three sweep variants behind ccg_opts.hessian_fp64, all with FP64 residual, cost and gradient:
-//       0 (default) k_intr_sweep_tc, intr_tc.cuh: warp-specialised, J'J on the TF32 tensor cores
+//     (SoA as uploaded, and re-packed into 640-byte blocks of 32 for the default sweep)
+//   * two sweep variants behind ccg_opts.hessian_fp64, both with FP64 residual, cost and gradient:
+//       0 (default) k_intr_sweep_ws, intr_sweep.cuh: warp-specialised, J'J on the TF32 tensor cores
 //       1           k_intr_sweep below: everything FP64, a warp PAIR per view (warp A accumulates
 //                   V(21) g_v(6) W[:,fx fy px py](24) + cost, warp B W[:,k1 k2 p1 p2 k3](30) + U(35) +
 //                   g_u(9); lane-private accumulators, one transposing shuffle reduction per view)
-//       2           k_intr_sweep_mixed, intr_mixed.cuh: J'J with FP32 FFMAs
 //   * the 9x9 reduced system is summed from per-CTA partials in a fixed order, so results are
 //     bit-reproducible for a given launch geometry (and bit-identical on every rank of a partition)
 //   * accept/reject, trust-region update and termination run on the device; the host replays one LM
@@ -57,6 +57,8 @@ struct IntrState {
 
 struct IntrDev {
   const float *u, *v, *X, *Y, *Z;
+  const float* obs_blk;  // the same observations as 640-byte blocks of 32: u[32] v[32] X[32] Y[32] Z[32]
+  const int2* vmeta;     // per view (+ sentinel): first block, observations
   const int64_t* view_off;
   const WorkItem* items;
   double* pose[2];
@@ -342,8 +344,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_intr_sweep(IntrDev d, double
 }
 
 }  // namespace ccg
-#include "intr_mixed.cuh"
-#include "intr_tc.cuh"
+#include "intr_sweep.cuh"
 #include "intr_init.cuh"
 namespace ccg {
 
@@ -803,7 +804,6 @@ struct ccg_intr_problem {
   bool one_shot = false;             // created by ccg_intrinsics_solve*: runs once, no graph instantiation
   int2* d_item_ranges = nullptr;
   float* d_obs = nullptr;
-  int group = 32;                    // lanes per view in the mixed-precision sweep (8, 16 or 32)
   bool single_item = false;          // every problem is one work item (batch of small problems)
   std::vector<int64_t> problem_off;  // host copy
   std::vector<int64_t> problem_obs;  // observations per problem
@@ -851,14 +851,12 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   p->n_obs = n_obs;
   cudaStream_t st = ctx->stream;
 
-  // lanes per view in the mixed sweep: small views share a warp (8 or 16 lanes each)
-  const double mean_obs = n_views > 0 ? (double)n_obs / (double)n_views : 0.0;
-  p->group = mean_obs <= 96.0 ? 8 : (mean_obs <= 224.0 ? 16 : 32);
   // ---- work items: consecutive views of one problem per CTA
   // one CTA per SM for a big problem (255-register kernels: one resident CTA per SM, so more
   // items only add wave-quantisation tail); small problems get one item each
   const int64_t target_items = (int64_t)ctx->sm_count;
   int64_t vpi = std::max<int64_t>(kWarps / 2, (n_views + target_items - 1) / std::max<int64_t>(target_items, 1));
+  vpi = std::min<int64_t>(vpi, kSwMaxViews);  // the default sweep keeps a per-view table of its item in shared memory
   std::vector<WorkItem> items;
   std::vector<int2> ranges((size_t)n_problems);
   p->problem_off.assign(problem_offsets, problem_offsets + n_problems + 1);
@@ -933,6 +931,26 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   CCG_CUDA(ctx, cudaMemcpyAsync(obs + 4 * n_obs, Z + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
   std::vector<int64_t> voff((size_t)n_views + 1);
   for (int64_t i = 0; i <= n_views; ++i) voff[(size_t)i] = view_offsets[i] - o0;
+  // block layout of the default sweep: every view padded to whole 32-observation blocks
+  std::vector<int2> vmeta((size_t)n_views + 1);
+  int64_t n_blocks = 0;
+  for (int64_t i = 0; i < n_views; ++i) {
+    const int64_t n = view_offsets[i + 1] - view_offsets[i];
+    if (n > 0x7fffffff || n_blocks > 0x7fffffff) return set_error(ctx, CCG_ERR_UNSUPPORTED, "view or problem too large");
+    vmeta[(size_t)i].x = (int)n_blocks;
+    vmeta[(size_t)i].y = (int)n;
+    n_blocks += (n + 31) / 32;
+  }
+  if (n_blocks > 0x7fffffff) return set_error(ctx, CCG_ERR_UNSUPPORTED, "problem too large");
+  vmeta[(size_t)n_views].x = (int)n_blocks;
+  vmeta[(size_t)n_views].y = 0;
+  int2* d_vmeta = nullptr;
+  float* d_blk = nullptr;
+  CCG_TRY(dev_alloc(p, &d_vmeta, vmeta.size()));
+  CCG_TRY(dev_alloc(p, &d_blk, (size_t)std::max<int64_t>(n_blocks, 1) * kObsBlock));
+  d.vmeta = d_vmeta;
+  d.obs_blk = d_blk;
+  CCG_CUDA(ctx, cudaMemcpyAsync(d_vmeta, vmeta.data(), sizeof(int2) * vmeta.size(), cudaMemcpyHostToDevice, st));
   std::vector<double> pose((size_t)n_views * kPose, 0.0);
   for (int64_t i = 0; i < n_views; ++i) {
     for (int k = 0; k < 4; ++k) pose[(size_t)i * kPose + k] = q[i * 4 + k];
@@ -945,6 +963,10 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_intr0, intr, sizeof(double) * 9 * n_problems, cudaMemcpyHostToDevice, st));
   CCG_TRY(dev_alloc(p, &p->d_problem_off, (size_t)n_problems + 1));
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_problem_off, p->problem_off.data(), sizeof(int64_t) * (n_problems + 1), cudaMemcpyHostToDevice, st));
+  if (n_views > 0) {
+    k_intr_pack<<<(unsigned)((n_views * 32 + 255) / 256), 256, 0, st>>>(d, n_views, d_blk);
+    ctx->launches++;
+  }
   // max |measurement| per problem, computed on the device from the uploaded observations
   {
     unsigned* d_bits = nullptr;
@@ -976,36 +998,26 @@ int reset_problem(ccg_intr_problem* p, const LmParams& P) {
 enum { TAG_SWEEP = 0, TAG_SCHUR = 1, TAG_SMALL = 2 };
 
 template <bool RES>
-void launch_sweep_tc_t(ccg_intr_problem* p, double* res_out) {
-  static bool attr_set = false;  // per process; the attribute is per device function
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_intr_sweep_tc<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-    attr_set = true;
+void launch_sweep_ws_t(ccg_intr_problem* p, double* res_out) {
+  ccg_ctx* ctx = p->ctx;
+  if (!ctx->sweep_attr[RES ? 1 : 0]) {  // per context: the attribute is per device
+    cudaFuncSetAttribute(k_intr_sweep_ws<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmem);
+    ctx->sweep_attr[RES ? 1 : 0] = true;
   }
-  k_intr_sweep_tc<RES><<<p->n_items, kTcWarps * 32, kTcSmem, p->ctx->stream>>>(p->dev, res_out);
+  k_intr_sweep_ws<RES><<<p->n_items, kSwThreads, kSwSmem, ctx->stream>>>(p->dev, res_out);
 }
 
-// candidate poses (back-substitution), then the warp-specialised sweep
-void launch_sweep_tc(ccg_intr_problem* p, double* res_out) {
-  k_intr_step<<<p->n_items * p->dev.schur_split, kStepThreads, 0, p->ctx->stream>>>(p->dev);
-  p->ctx->launches++;
-  if (res_out) launch_sweep_tc_t<true>(p, res_out);
-  else launch_sweep_tc_t<false>(p, res_out);
-}
-
-// the sweep kernel variant: FP64 warp pairs, or mixed precision with G lanes per view
+// the sweep kernel variant: warp-specialised tensor-core sweep (after the candidate-pose kernel), or
+// everything in FP64 with a warp pair per view
 void launch_sweep(ccg_intr_problem* p, const LmParams& P, double* res_out) {
   cudaStream_t st = p->ctx->stream;
   if (P.hessian_fp64 == 0) {
-    launch_sweep_tc(p, res_out);
-  } else if (P.hessian_fp64 == 1) {
-    k_intr_sweep<<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
-  } else if (p->group == 8) {
-    k_intr_sweep_mixed<8><<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
-  } else if (p->group == 16) {
-    k_intr_sweep_mixed<16><<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
+    k_intr_step<<<p->n_items * p->dev.schur_split, kStepThreads, 0, st>>>(p->dev);
+    p->ctx->launches++;
+    if (res_out) launch_sweep_ws_t<true>(p, res_out);
+    else launch_sweep_ws_t<false>(p, res_out);
   } else {
-    k_intr_sweep_mixed<32><<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
+    k_intr_sweep<<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
   }
   p->ctx->launches++;
 }

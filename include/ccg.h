@@ -55,7 +55,7 @@ typedef struct {
   int32_t hessian_fp64;         /* single-camera sweep variant.  Residual, cost and gradient are FP64 in all of them (same
                                    fixed point); they differ in how the J'J blocks are formed:
                                    0 (default) TF32 tensor-core products of float32 Jacobian rows, 1 everything in
-                                   FP64, 2 float32 FFMA products */
+                                   FP64 */
   int32_t reserved_;
 } ccg_opts;
 
@@ -165,8 +165,8 @@ int ccg_distort(ccg_ctx* ctx, const float* xn, const float* yn, int64_t n, const
  *   res 2/obs | Vb 36/view (6x6) | Wb 54/view (6x9) | gvb 6/view | U 81 | gu 9 | cost 1
  * Tangent order per view: rotation (half-angle vector, Ceres QuaternionManifold
  * convention) then translation.  hessian_fp64 selects the sweep variant (see ccg_opts): with 0
- * V, W, U are TF32 tensor-core products (~1e-3 relative), with 2 FP32 (~1e-6); res, gvb, gu and
- * cost are FP64 in every variant. */
+ * V, W, U are TF32 tensor-core products (~1e-3 relative), with 1 FP64; res, gvb, gu and cost are
+ * FP64 in both. */
 int ccg_intrinsics_eval(ccg_ctx* ctx, const float* u, const float* v, const float* X,
                         const float* Y, const float* Z, const int64_t* view_offsets,
                         int64_t n_views, const double* intr, const double* q, const double* t,

@@ -22,20 +22,19 @@ def _check_solution(got, ref, poses=True):
         assert rel_err(gt, rt, floor=1e-3) <= TOL_PARAM
 
 
-@pytest.mark.parametrize("mode,npts", [(1, 54), (0, 54), (0, 150), (0, 400), (0, 33), (2, 54), (2, 150), (2, 400)])
+@pytest.mark.parametrize("mode,npts", [(1, 54), (0, 54), (0, 150), (0, 400), (0, 33), (1, 150)])
 def test_eval_blocks_match_oracle(ctx, mode, npts):
     """r, V, W, g_v, U, g_u, cost of one sweep at the Estimate() starting point.  Residuals, cost
     and gradients are FP64 in every sweep variant (1e-11).  The J'J blocks are FP64 (mode 1: 1e-11),
-    TF32 tensor-core products of float32 Jacobian rows in the default sweep (mode 0: operands
-    truncated to 11 significant bits by design, 3e-3 of the block's largest entry), or float32
-    FFMA products (mode 2: 3e-6).  The view sizes exercise partial 32-observation chunks and the
-    8-, 16- and 32-lane-per-view instantiations of mode 2."""
+    or TF32 tensor-core products of float32 Jacobian rows in the default sweep (mode 0: operands
+    truncated to 11 significant bits by design, 3e-3 of the block's largest entry).  The view sizes
+    exercise partial 32-observation blocks."""
     d = oracle.datagen_planar(20, npts)
     intr, q, t = start_from_estimate(oracle, d)
     intr[4:] = [-0.03, 0.002, 0.001, -0.0005, 0.0007]  # exercise every Jacobian column
     g = ctx.intrinsics_eval(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t, hessian_fp64=mode)
     r = oracle.intrinsics_eval(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
-    tol_h = {0: 3e-3, 1: 1e-11, 2: 3e-6}[mode]
+    tol_h = {0: 3e-3, 1: 1e-11}[mode]
     assert np.max(np.abs(g["res"] - r["res"])) <= 1e-9 * max(1.0, np.max(np.abs(r["res"])))
     assert abs(g["cost"] - r["cost"]) <= 1e-12 * r["cost"]
     assert block_err(g["gu"], r["gu"]) <= 1e-11
@@ -46,10 +45,10 @@ def test_eval_blocks_match_oracle(ctx, mode, npts):
             assert block_err(g[key][i], r[key][i]) <= tol_h, (key, i)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1])
 def test_solve_c1_from_estimate(ctx, mode):
-    """Config C1: 20 views x 54 points, Estimate() initialisation, all nine intrinsics free; every
-    sweep variant (tensor-core = default, all-FP64, FP32 FFMA) must land on the oracle's minimum."""
+    """Config C1: 20 views x 54 points, Estimate() initialisation, all nine intrinsics free; both
+    sweep variants (tensor-core = default, all-FP64) must land on the oracle's minimum."""
     import camera_calibrator_b200 as cc
 
     d = oracle.datagen_planar(20, 54)

@@ -1,5 +1,5 @@
-"""Time the sweep kernel alone (CUDA events inside libccg.so) on a C5-geometry problem.
-Usage: python tools/time_sweep.py [views] [points]   (CCG_TC_WARPS selects the tc variant)"""
+"""Time the sweep kernel alone (CUDA events inside libccg.so) and one full device-resident solve on a
+C5-geometry problem.  Usage: python tools/time_sweep.py [views] [points]   (CCG_LIB selects a variant build)"""
 import os
 import sys
 
@@ -15,5 +15,10 @@ intr, q, t = synth.perturbed_start(d)
 p = ctx.intrinsics_problem(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr, q, t)
 ms = p.time_sweep(10)
 gb = (20.0 * d.n_obs + 704.0 * d.n_views) / 1e9
-print(f"CCG_TC_WARPS={os.environ.get('CCG_TC_WARPS', 'default')} views {nv} x {npts}: sweep {ms:.4f} ms/launch, "
-      f"{gb / (ms * 1e-3):.1f} GB/s algorithmic, {d.n_obs / (ms * 1e-3) / 1e9:.2f} Gobs/s")
+lib = os.path.basename(os.environ.get("CCG_LIB", "libccg.so"))
+print(f"{lib} views {nv} x {npts}: sweep {ms:.4f} ms/launch, "
+      f"{gb / (ms * 1e-3):.1f} GB/s algorithmic, {d.n_obs / (ms * 1e-3) / 1e9:.2f} Gobs/s", flush=True)
+p.run()
+tm = p.run()
+got = p.download()
+print(f"   solve {tm['total_ms']:.3f} ms  intr {got[0][0][:4]} k {got[0][0][4:]} report {got[3][0]}", flush=True)
