@@ -55,6 +55,8 @@ int set_error(ccg_ctx* ctx, int status, const char* what, cudaError_t e = cudaSu
   } while (0)
 
 int nccl_allreduce_sum(ccg_ctx* ctx, double* buf, size_t count);
+int nccl_allreduce_max(ccg_ctx* ctx, double* buf, size_t count);
+int peer_resync(ccg_ctx* ctx, double* scratch);  // scratch: one device double
 
 // --------------------------------------------------------------------------
 // Allreduce of 64 doubles over peer memory (NVLink / NVSwitch), fused into the kernel that needs
@@ -309,7 +311,9 @@ __device__ inline void peer_allreduce64(double* s_vals, const PeerComm& pc) {
   if (tid < kPeerVals) {
     double acc = 0.0;
     for (int src = 0; src < pc.world; ++src) acc += __ldcg(&pc.box[pc.rank][par * kPeerMaxWorld + src].data[tid]);
-    s_vals[tid] = s_timeout ? nan("") : acc;
+    // a peer that never showed up: poison the sums and raise the failure flag (slot 63 is unused by both
+    // reduced-system layouts); the consumer stops with CCG_ERR_NCCL instead of treating NaN as a bad step
+    s_vals[tid] = s_timeout ? (tid == kPeerVals - 1 ? -1.0 : nan("")) : acc;
   }
   __syncthreads();
   if (tid == 0) *pc.seq = seq;

@@ -72,6 +72,14 @@ int nccl_allreduce_sum(ccg_ctx* ctx, double* buf, size_t count) {
   return CCG_OK;
 }
 
+int nccl_allreduce_max(ccg_ctx* ctx, double* buf, size_t count) {
+  if (!ctx->nccl_comm) return set_error(ctx, CCG_ERR_NCCL, "no communicator");
+  // ncclFloat64 = 8, ncclMax = 2 (stable enum values of nccl.h)
+  const int rc = g_nccl.AllReduce(buf, buf, count, 8, 2, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return set_error(ctx, CCG_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllReduce");
+  return CCG_OK;
+}
+
 // ---------------------------------------------------------- memory pool ----
 cudaError_t pool_alloc(ccg_ctx* ctx, void** out, size_t bytes) {
   if (bytes == 0) bytes = 1;
@@ -141,6 +149,22 @@ static void setup_peer_mailboxes(ccg_ctx* ctx) {
     cudaMemcpy(&bad, d_ok, sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d_ok);
   ctx->peer_ok = bad == 0.0;
+}
+
+// Line the ranks of a partitioned solve up (a collective that waits without a deadline) and agree on
+// the sequence number of the peer-memory allreduces: after a timeout or a host-side error on one rank
+// the rank-local counters differ, and every later allreduce would wait for a number nobody publishes.
+__global__ void k_peer_seq_get(const unsigned long long* seq, double* out) { out[0] = (double)(*seq); }
+__global__ void k_peer_seq_set(unsigned long long* seq, const double* agreed) {
+  *seq = (unsigned long long)agreed[0] + 2ull;  // beyond anything a straggler may still publish
+}
+int peer_resync(ccg_ctx* ctx, double* scratch) {
+  k_peer_seq_get<<<1, 1, 0, ctx->stream>>>(ctx->d_seq, scratch);
+  const int rc = nccl_allreduce_max(ctx, scratch, 1);
+  if (rc != CCG_OK) return rc;
+  k_peer_seq_set<<<1, 1, 0, ctx->stream>>>(ctx->d_seq, scratch);
+  ctx->launches += 2;
+  return CCG_OK;
 }
 
 // ------------------------------------------------------------ profiler ----

@@ -64,7 +64,8 @@ struct IntrDev {
   double* pose[2];
   double* blk[2];
   double* yz;
-  double* rt;         // candidate pose as rotation matrix + translation, 12 doubles per view (tensor-core sweep)
+  double* rt;         // candidate pose as rotation matrix + translation, 12 doubles per view (default sweep, FP64 role)
+  float* rtf;         // the same in float32 (Jacobian role)
   double* step_part;  // g'd, d'Dd partials of the candidate-pose kernel: [item * schur_split + sub][2]
   double* sweep_part;
   double* schur_part;
@@ -574,6 +575,10 @@ __device__ inline void decide_body(IntrState& ps, const LmParams& P, bool evalua
     if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, n_done, true);
     return;
   }
+  if (r[kSweepPart - 1] < 0.0) {  // the peer-memory allreduce timed out
+    lm_finish(s, CCG_ERR_NCCL, n_done, false);
+    return;
+  }
   const double cost_c = 0.5 * r[0];
   const bool accept = lm_decide(s, P, cost_c, r[7] + s.gTd_u, r[8] + s.dDd_u, n_done);
   if (accept) {
@@ -610,6 +615,11 @@ __device__ inline void solve_body(IntrState& ps, const LmParams& P, const double
   LmState& s = ps.lm;
   const unsigned mask = ps.mask;
   const int par = s.par;
+  if (r[kSchurPart - 1] < 0.0) {  // the peer-memory allreduce timed out
+    s.finalize = 0;
+    if (s.status == 0) lm_finish(s, CCG_ERR_NCCL, n_done, false);
+    return;
+  }
   double gDg = r[54];
   for (int k = 0; k < 9; ++k)
     if (!((mask >> k) & 1u) && ps.U[k * 9 + k] > 0.0) gDg += ps.gu[k] * ps.gu[k] / ps.U[k * 9 + k];
@@ -856,7 +866,6 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   // items only add wave-quantisation tail); small problems get one item each
   const int64_t target_items = (int64_t)ctx->sm_count;
   int64_t vpi = std::max<int64_t>(kWarps / 2, (n_views + target_items - 1) / std::max<int64_t>(target_items, 1));
-  vpi = std::min<int64_t>(vpi, kSwMaxViews);  // the default sweep keeps a per-view table of its item in shared memory
   std::vector<WorkItem> items;
   std::vector<int2> ranges((size_t)n_problems);
   p->problem_off.assign(problem_offsets, problem_offsets + n_problems + 1);
@@ -906,6 +915,7 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   const int schur_split = (int)std::max<int64_t>(1, std::min<int64_t>((max_item_views + 63) / 64, 32));
   CCG_TRY(dev_alloc(p, &d.schur_part, items.size() * (size_t)schur_split * kSchurPart));
   CCG_TRY(dev_alloc(p, &d.rt, (size_t)n_views * 12));
+  CCG_TRY(dev_alloc(p, &d.rtf, (size_t)n_views * 12));
   CCG_TRY(dev_alloc(p, &d.step_part, items.size() * (size_t)schur_split * 2));
   CCG_TRY(dev_alloc(p, &d.red_sweep, (size_t)n_problems * kSweepPart));
   CCG_TRY(dev_alloc(p, &d.red_schur, (size_t)n_problems * kSchurPart));
@@ -975,6 +985,9 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
     k_intr_meas_scale<<<p->n_items, 256, 0, st>>>(d, d_bits);
     k_intr_meas_finish<<<(int)((n_problems + 127) / 128), 128, 0, st>>>(d_bits, p->d_meas_scale, (int)n_problems);
     ctx->launches += 2;
+    // a partitioned calibration: the scale feeds the accept/reject thresholds of lm_decide, and every rank
+    // must take the same branch - the maximum is over ALL ranks' observations
+    if (shared && ctx->world > 1) CCG_TRY(nccl_allreduce_max(ctx, p->d_meas_scale, (size_t)n_problems));
   }
   CCG_CUDA(ctx, cudaStreamSynchronize(st));  // host staging vectors go out of scope
   return CCG_OK;
@@ -1119,7 +1132,8 @@ int run_problem(ccg_intr_problem* p, const ccg_opts& opts, ccg_timing* timing) {
   if (p->shared && ctx->world > 1 && ctx->peer_ok) {
     // line the ranks up once per solve with a collective that waits without a deadline; the
     // peer-memory allreduces inside the kernels then only see the skew of one LM iteration
-    CCG_TRY(nccl_allreduce_sum(ctx, p->dev.red_sweep, 1));
+    // (the same collective re-synchronises the sequence numbers of those allreduces)
+    CCG_TRY(peer_resync(ctx, p->dev.red_sweep));
     n_allreduce++;
   }
   CCG_TRY(launch_sweep_decide(p, P, prof, nullptr, &n_allreduce));

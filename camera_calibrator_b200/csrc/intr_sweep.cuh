@@ -13,25 +13,22 @@
 //                the B fragment (the product is J'J), so a k-step costs two LDS.64.
 //
 // Roles (one CTA per SM, one work item = a range of views per CTA):
-//   * every SM sub-partition runs ONE FP64-role warp (the highest warp ids: the issue arbiter
-//     prefers them) and kSwJPD Jacobian-role warps.  The FP64 role is bound by the FP64 pipe
-//     (~90 two-cycle instructions per 32 observations) and needs registers, not warps; the Jacobian
-//     role is a long chain of dependent FP32 -> STS -> LDS -> HMMA and needs warps, not registers.
-//     setmaxnreg moves the registers accordingly (FP64 warps kSwRegD, Jacobian warps kSwRegJ).
-//   * the four groups of a CTA split the item's views into four ranges; inside a group the FP64
-//     warp walks every view of the range and Jacobian warp j the views j, j + kSwJPD, ... - so all
-//     warps of a group stay within a few views of each other and the second reader of an
-//     observation block hits L1/L2 (HBM traffic stays 20 B per observation).  Roles share nothing
-//     but the read-only inputs: no synchronisation inside the loops.
+//   * the CTA runs kSwPairs warp PAIRS, two per SM sub-partition: an FP64-role warp (the higher warp
+//     ids: the issue arbiter prefers them) and a Jacobian-role warp that walk the SAME contiguous
+//     range of views, each on its own - they share nothing but the read-only inputs, so there is no
+//     synchronisation inside the loops, and the second reader of an observation block hits L1/L2
+//     (HBM traffic stays 20 B per observation).  setmaxnreg gives the FP64 warps kSwRegD registers
+//     and leaves the Jacobian warps kSwRegJ.
 //
 // Observation stream: the observations live in HBM as 640-byte blocks of 32 observations
 // (u[32] v[32] X[32] Y[32] Z[32], views padded to whole blocks with zeros), so a 32-observation
-// chunk is ONE aligned block: two 16-byte cp.async per lane fetch it (one for the Jacobian role,
-// which reads X Y Z only) into a small per-warp ring of stages, kSwAhead* chunks ahead of the
-// one being consumed.  A stage also carries the pose of the chunk's view when the chunk is the
-// first of its view (rotation matrix + translation, written by k_intr_step) and a descriptor
-// (view, valid observations, first/last flags) written by the prefetch cursor, so the consumer
-// loop is flat: wait, read the descriptor, compute, and at a view's last chunk run the epilogue.
+// chunk is ONE aligned block and the blocks of a warp's view range are one contiguous stream:
+// two 16-byte cp.async per lane (one for the Jacobian role, which reads X Y Z only) fetch block
+// k + kSwAhead* into a small per-warp ring while block k is consumed - no view logic on that path.
+// A warp loads the NEXT chunk's observation into registers before it computes the current one
+// (shared-memory latency off the dependent chain).  Loops: views outside (pose and size of the next
+// view are fetched one view ahead with plain loads), full chunks inside, the partial last chunk of
+// a view peeled off, so the inner loops carry no masking and no view bookkeeping.
 //
 // Operand precision: the raw float32 rows are fed to the TF32 unit (10 explicit mantissa bits).
 // tools/h_precision_study.py shows that the exact-Schur LM takes the same iterations with such
@@ -44,49 +41,54 @@
 
 namespace ccg {
 
-#ifndef CCG_SW_JPD
-#define CCG_SW_JPD 4
-#endif
-constexpr int kSwD = 4;               // FP64-role warps, one per SM sub-partition
-constexpr int kSwJPD = CCG_SW_JPD;    // Jacobian-role warps per FP64-role warp
-constexpr int kSwJ = kSwD * kSwJPD;   // Jacobian-role warps (warps 0 .. kSwJ-1)
-constexpr int kSwWarps = kSwJ + kSwD;
+constexpr int kSwPairs = 8;              // (FP64 warp, Jacobian warp) pairs per CTA, two per SM sub-partition
+constexpr int kSwWarps = 2 * kSwPairs;   // warps 0 .. kSwPairs-1: Jacobian role; the rest: FP64 role
 constexpr int kSwThreads = kSwWarps * 32;
-// register budgets: the CTA is launched with kSwRegLaunch registers per thread; the Jacobian
-// warpgroups give registers back (setmaxnreg.dec) and the FP64 warpgroup takes them (.inc)
+// register budgets: the CTA is launched with 128 registers per thread; the Jacobian warpgroups give
+// registers back (setmaxnreg.dec) and the FP64 warpgroups take them (.inc)
 constexpr int kSwRegLaunch = (65536 / kSwThreads) & ~7;
 #ifndef CCG_SW_REGJ
-#define CCG_SW_REGJ (CCG_SW_JPD >= 4 ? 80 : 96)
+#define CCG_SW_REGJ 104
 #endif
 constexpr int kSwRegJ = CCG_SW_REGJ;
-constexpr int kSwRegD = ((kSwRegLaunch * kSwThreads - kSwRegJ * kSwJ * 32) / (kSwD * 32)) & ~7;
-static_assert(kSwRegD >= 128 && kSwRegD <= 256 && kSwRegJ % 8 == 0, "register split");
-static_assert(kSwD == 4, "one setmaxnreg warpgroup of FP64 warps");
+constexpr int kSwRegD = 2 * kSwRegLaunch - kSwRegJ;
+static_assert(kSwRegD >= kSwRegLaunch && kSwRegD <= 256 && kSwRegJ % 8 == 0, "register split");
 
 #ifndef CCG_SW_AHEAD_D
 #define CCG_SW_AHEAD_D 6
 #endif
 #ifndef CCG_SW_AHEAD_J
-#define CCG_SW_AHEAD_J 2
+#define CCG_SW_AHEAD_J 4
 #endif
-constexpr int kSwAheadD = CCG_SW_AHEAD_D, kSwStagesD = kSwAheadD + 2;  // chunks in flight / ring size
+constexpr int kSwAheadD = CCG_SW_AHEAD_D, kSwStagesD = kSwAheadD + 2;  // blocks in flight / ring size
 constexpr int kSwAheadJ = CCG_SW_AHEAD_J, kSwStagesJ = kSwAheadJ + 2;
-constexpr int kSwStageD = 192;  // floats: u v X Y Z (160) | pose (24) | descriptor (4) | pad (4)
-constexpr int kSwStageJ = 128;  // floats: X Y Z (96) | pose (24) | descriptor (4) | pad (4)
-constexpr int kSwMaxViews = 2048;  // views per work item (per-view table in shared memory)
-constexpr int kObsBlock = 160;     // floats per 32-observation block in HBM
+// chunks a warp works on at a time: 2 = two independent dependency chains per lane (the FP64 pipe needs ~4
+// chains per SM sub-partition to be busy: DFMA latency 8 cycles, issue interval 2.2, tools/ubench_dfma_latency.cu)
+#ifndef CCG_SW_D2
+#define CCG_SW_D2 1
+#endif
+#ifndef CCG_SW_J2
+#define CCG_SW_J2 1
+#endif
+constexpr bool kSwD2 = CCG_SW_D2 != 0, kSwJ2 = CCG_SW_J2 != 0;
+// The FP64 role is the slower one when both run, so a Jacobian warp also runs the FP64 role on the last
+// kSwTail / 64 of its pair's views once its own work is done (static split: sums stay bit-reproducible).
+#ifndef CCG_SW_TAIL
+#define CCG_SW_TAIL 12
+#endif
+constexpr int kSwTail = CCG_SW_TAIL;
+constexpr int kSwTiles = kSwJ2 ? 2 : 1;  // Jacobian-row tiles per Jacobian warp
+constexpr int kObsBlock = 160;   // floats per 32-observation block in HBM: u v X Y Z
+constexpr int kSwStageD = 160;   // floats per stage: the whole block
+constexpr int kSwStageJ = 96;    // floats per stage: X Y Z
 
 constexpr int kTcRow = 20;            // floats per Jacobian row in the tile (16 + 4: conflict-free STS.128 and LDS.64)
 constexpr int kTcTile = 64 * kTcRow;  // one 32-observation tile
-#ifndef CCG_SW_TILES
-#define CCG_SW_TILES 1
-#endif
-constexpr int kSwTiles = CCG_SW_TILES;  // tiles per Jacobian warp (2: chunk j's rows are computed while j-1 is contracted)
 
-constexpr size_t kSwSmem = sizeof(double) * kSwWarps * kSweepPart + sizeof(int2) * kSwMaxViews +
-                           sizeof(float) * (kSwD * kSwStagesD * kSwStageD + kSwJ * kSwStagesJ * kSwStageJ +
-                                            kSwJ * kSwTiles * kTcTile);
+constexpr size_t kSwSmem = sizeof(double) * kSwWarps * kSweepPart +
+                           sizeof(float) * kSwPairs * (kSwStagesD * kSwStageD + kSwStagesJ * kSwStageJ + kSwTiles * kTcTile);
 static_assert(kSwSmem <= 227 * 1024, "shared memory");
+static_assert(kSwTail == 0 || kSwTiles * kTcTile >= kSwStagesD * kSwStageD, "the FP64 tail's ring lives in the tile(s)");
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], unsigned a0, unsigned a1, unsigned a2,
                                                 unsigned a3, unsigned b0, unsigned b1) {
@@ -143,7 +145,7 @@ struct TcConst32 {
 // zero observation (finite arithmetic) and its residual is forced to zero, so it contributes
 // nothing.  res (RES only): where this lane's residual pair goes.
 // ---------------------------------------------------------------------------------------------
-template <bool RES>
+template <bool RES, bool MASK>
 __device__ __forceinline__ void tc_fp64_observation(const TcConst64& K, const double (&R)[9], const double (&t)[3],
                                                     float mu, float mv, float Xf, float Yf, float Zf, bool valid,
                                                     double (&gu)[9], double (&gv)[6], double& cost,
@@ -165,8 +167,10 @@ __device__ __forceinline__ void tc_fp64_observation(const TcConst64& K, const do
   const double yd = fma(yn, m, fma(K.p2, a1, K.p1 * a3));
   double ru = fma(K.fx, xd, K.cx - dmu);
   double rv = fma(K.fy, yd, K.cy - dmv);
-  ru = valid ? ru : 0.0;
-  rv = valid ? rv : 0.0;
+  if (MASK) {
+    ru = valid ? ru : 0.0;
+    rv = valid ? rv : 0.0;
+  }
   if (RES) {
     if (valid) {
       res[0] = ru;
@@ -203,15 +207,110 @@ __device__ __forceinline__ void tc_fp64_observation(const TcConst64& K, const do
   gv[2] = fma(pt0, w1, fma(-pt1, w0, gv[2]));
 }
 
+// N observations per lane at a time (N full chunks), written statement by statement across the N
+// observations so that the instruction stream interleaves N independent dependency chains (ptxas keeps
+// two separately written observations one after the other; DFMA has a latency of 8 cycles and the FP64
+// pipe issues a warp instruction every 2.2 cycles, tools/ubench_dfma_latency.cu).  No masking.
+template <bool RES, int N>
+__device__ __forceinline__ void tc_fp64_observations(const TcConst64& K, const double (&R)[9], const double (&t)[3],
+                                                     const float (&muf)[N], const float (&mvf)[N], const float (&Xf)[N],
+                                                     const float (&Yf)[N], const float (&Zf)[N], double (&gu)[9],
+                                                     double (&gv)[6], double& cost, double* __restrict__ res) {
+#define CCG_EACH for (int k = 0; k < N; ++k)
+  double X[N], Y[N], Z[N], dmu[N], dmv[N], pt0[N], pt1[N], pt2[N], iz[N], xn[N], yn[N], xx[N], yy[N], xy[N], r2[N], r4[N],
+      r6[N], h2[N], h1[N], m[N], mp[N], a1[N], a2[N], a3[N], xd[N], yd[N], ru[N], rv[N], tu[N], tv[N], sr[N], tx[N], ty[N],
+      u1[N], u2[N], base[N], F00[N], F01[N], F11[N], w0[N], w1[N], w2[N];
+#pragma unroll
+  CCG_EACH { X[k] = (double)Xf[k]; Y[k] = (double)Yf[k]; Z[k] = (double)Zf[k]; }
+#pragma unroll
+  CCG_EACH pt2[k] = fma(R[6], X[k], fma(R[7], Y[k], fma(R[8], Z[k], t[2])));
+#pragma unroll
+  CCG_EACH pt0[k] = fma(R[0], X[k], fma(R[1], Y[k], fma(R[2], Z[k], t[0])));
+#pragma unroll
+  CCG_EACH pt1[k] = fma(R[3], X[k], fma(R[4], Y[k], fma(R[5], Z[k], t[1])));
+#pragma unroll
+  CCG_EACH iz[k] = fast_rcp(pt2[k]);
+#pragma unroll
+  CCG_EACH { dmu[k] = (double)muf[k]; dmv[k] = (double)mvf[k]; }
+#pragma unroll
+  CCG_EACH { xn[k] = pt0[k] * iz[k]; yn[k] = pt1[k] * iz[k]; }
+#pragma unroll
+  CCG_EACH { xx[k] = xn[k] * xn[k]; yy[k] = yn[k] * yn[k]; xy[k] = xn[k] * yn[k]; }
+#pragma unroll
+  CCG_EACH { r2[k] = xx[k] + yy[k]; a1[k] = xy[k] + xy[k]; }
+#pragma unroll
+  CCG_EACH { h2[k] = fma(r2[k], K.k3, K.k2); r4[k] = r2[k] * r2[k]; a2[k] = fma(2.0, xx[k], r2[k]); a3[k] = fma(2.0, yy[k], r2[k]); }
+#pragma unroll
+  CCG_EACH { h1[k] = fma(r2[k], h2[k], K.k1); r6[k] = r4[k] * r2[k]; }
+#pragma unroll
+  CCG_EACH { m[k] = fma(r2[k], h1[k], 1.0); mp[k] = fma(r2[k], fma(r2[k], K.k3, h2[k]), h1[k]); }
+#pragma unroll
+  CCG_EACH {
+    xd[k] = fma(xn[k], m[k], fma(K.p1, a1[k], K.p2 * a2[k]));
+    yd[k] = fma(yn[k], m[k], fma(K.p2, a1[k], K.p1 * a3[k]));
+  }
+#pragma unroll
+  CCG_EACH { ru[k] = fma(K.fx, xd[k], K.cx - dmu[k]); rv[k] = fma(K.fy, yd[k], K.cy - dmv[k]); }
+  if (RES) {
+#pragma unroll
+    CCG_EACH { res[64 * k] = ru[k]; res[64 * k + 1] = rv[k]; }
+  }
+#pragma unroll
+  CCG_EACH { tu[k] = K.fx * ru[k]; tv[k] = K.fy * rv[k]; }  // d cost / d(xd, yd)
+#pragma unroll
+  CCG_EACH { tx[k] = xn[k] + xn[k]; ty[k] = yn[k] + yn[k]; }
+#pragma unroll
+  CCG_EACH { u1[k] = K.p1 * ty[k]; u2[k] = K.p2 * tx[k]; sr[k] = fma(xn[k], tu[k], yn[k] * tv[k]); }
+#pragma unroll
+  CCG_EACH base[k] = m[k] + (u1[k] + u2[k]);
+  // d(xd,yd)/d(xn,yn): F00 = m + 2xx mp + 2p1 yn + 6p2 xn, F01 = a1 mp + 2p1 xn + 2p2 yn, F11 = m + 2yy mp + 2p2 xn + 6p1 yn
+#pragma unroll
+  CCG_EACH {
+    F00[k] = fma(2.0, u2[k], fma(a2[k] - r2[k], mp[k], base[k]));
+    F01[k] = fma(a1[k], mp[k], fma(K.p1, tx[k], K.p2 * ty[k]));
+    F11[k] = fma(2.0, u1[k], fma(a3[k] - r2[k], mp[k], base[k]));
+  }
+#pragma unroll
+  CCG_EACH {  // d cost / d(pt0, pt1, pt2)
+    w0[k] = fma(F00[k], tu[k], F01[k] * tv[k]) * iz[k];
+    w1[k] = fma(F01[k], tu[k], F11[k] * tv[k]) * iz[k];
+  }
+#pragma unroll
+  CCG_EACH w2[k] = -fma(xn[k], w0[k], yn[k] * w1[k]);
+  // accumulation: the sums are taken in observation order, as the one-observation path does
+#pragma unroll
+  CCG_EACH {
+    cost = fma(ru[k], ru[k], fma(rv[k], rv[k], cost));
+    gu[0] = fma(xd[k], ru[k], gu[0]);
+    gu[1] = fma(yd[k], rv[k], gu[1]);
+    gu[2] += ru[k];
+    gu[3] += rv[k];
+    gu[4] = fma(r2[k], sr[k], gu[4]);
+    gu[5] = fma(r4[k], sr[k], gu[5]);
+    gu[8] = fma(r6[k], sr[k], gu[8]);
+    gu[6] = fma(a1[k], tu[k], fma(a3[k], tv[k], gu[6]));
+    gu[7] = fma(a2[k], tu[k], fma(a1[k], tv[k], gu[7]));
+    gv[3] += w0[k];
+    gv[4] += w1[k];
+    gv[5] += w2[k];
+    // rotation tangent: 2 (y x w) with y = pt - t; accumulated as pt x w, fixed up per view
+    gv[0] = fma(pt1[k], w2[k], fma(-pt2[k], w1[k], gv[0]));
+    gv[1] = fma(pt2[k], w0[k], fma(-pt0[k], w2[k], gv[1]));
+    gv[2] = fma(pt0[k], w1[k], fma(-pt1[k], w0[k], gv[2]));
+  }
+#undef CCG_EACH
+}
+
 // ---------------------------------------------------------------------------------------------
 // Jacobian role: the two float32 Jacobian rows of one observation per lane, in tile order.
 // Invalid lanes produce all-zero rows.
 // ---------------------------------------------------------------------------------------------
+template <bool MASK>
 __device__ __forceinline__ void tc_fp32_rows(const TcConst32& K, const float (&Rf)[9], const float (&tf)[3],
                                              float X, float Y, float Z, bool valid, float4 (&ur)[4],
                                              float4 (&vr)[4]) {
-  const float one = valid ? 1.0f : 0.0f;
-  const float fxv = valid ? K.fx : 0.0f, fyv = valid ? K.fy : 0.0f;
+  const float one = (!MASK || valid) ? 1.0f : 0.0f;
+  const float fxv = (!MASK || valid) ? K.fx : 0.0f, fyv = (!MASK || valid) ? K.fy : 0.0f;
   const float y0 = fmaf(Rf[0], X, fmaf(Rf[1], Y, Rf[2] * Z));
   const float y1 = fmaf(Rf[3], X, fmaf(Rf[4], Y, Rf[5] * Z));
   const float y2 = fmaf(Rf[6], X, fmaf(Rf[7], Y, Rf[8] * Z));
@@ -337,144 +436,71 @@ __device__ __forceinline__ void tc_contract(unsigned frag, int nvalid, float (&c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Prefetch cursor of a role warp over its views (v0, v0 + STEP, ... < v_end, relative to the work
-// item's first view) and their 32-observation chunks.  An empty view yields one chunk with zero
-// valid observations, so its (all-zero) blocks are still written.  All fields are warp-uniform.
+// Block stream of a role warp: the blocks of its view range are contiguous in HBM.  next() requests
+// block k + AHEAD (if there is one) into the ring stage that was read two calls ago - every lane has
+// read it, the __syncwarp of the previous call came after those reads - commits one cp.async group
+// (so cp.async.wait_group counts blocks), waits for block k and returns the shared address of this
+// lane's observation in it; the caller reads its registers from there at once.  The ring has
+// AHEAD + 2 stages: AHEAD blocks in flight, the one being read, the one read one call ago.
 // ---------------------------------------------------------------------------------------------
-template <int STEP>
-struct SwCursor {
-  unsigned vm;  // shared address of the item's per-view table (first block, observations)
-  int v, v_end;
-  int blk, rem;  // block of the cursor's chunk; observations of the view from this chunk on
-  bool first, ok;
-  __device__ __forceinline__ void load() {
-    const int2 m = lds_v2s32(vm + 8u * (unsigned)v);
-    blk = m.x;
-    rem = m.y;
-    first = true;
-  }
-  __device__ __forceinline__ void init(unsigned vm_, int v0, int v_end_) {
-    vm = vm_;
-    v = v0;
-    v_end = v_end_;
-    blk = rem = 0;
-    first = false;
-    ok = v < v_end;
-    if (ok) load();
-  }
-  __device__ __forceinline__ void next() {
-    if (rem > 32) {
-      rem -= 32;
-      ++blk;
-      first = false;
-    } else {
-      v += STEP;
-      ok = v < v_end;
-      if (ok) load();
-    }
-  }
-};
-
-// chunk descriptor, one int: view (relative to the item) | valid observations << 12 | first << 20 | last << 21;
-// -1 = end of the warp's stream
-constexpr int kDescFirst = 1 << 20, kDescLast = 1 << 21;
-
-// Request the cursor's chunk into the stage at shared address `st` and advance the cursor: the
-// observation block (the X Y Z part only for the Jacobian role), the view's pose when the chunk
-// opens a view, and the descriptor.
-//   default: one bulk copy (TMA, cp.async.bulk) per block / pose issued by lane 0, completing on the
-//     stage's mbarrier (expect_tx bytes); the descriptor store precedes the arrive, so a lane that
-//     has seen the phase complete sees the descriptor too.
-//   CCG_SW_LDGSTS: 16-byte cp.async by the lanes, one commit group per call (wait_group counts chunks).
-// src = obs_blk (+ 256 for the Jacobian role), rt = rt(item's first view) (bytes).
-template <int NARR, int STEP>
-__device__ __forceinline__ void sw_issue(const char* src, const char* rt, unsigned st, SwCursor<STEP>& cur, int lane) {
-  constexpr unsigned kPoseOff = (NARR == 5 ? 160 : 96) * 4, kDescOff = kPoseOff + 96, kBarOff = kDescOff + 8;
-  constexpr unsigned kBytes = NARR == 5 ? 640 : 384;
-#ifdef CCG_SW_LDGSTS
-  if (cur.ok) {
-    const int nvalid = min(32, cur.rem);  // 0 for an empty view
-    const unsigned dst = st + 16u * (unsigned)lane;
-    if (nvalid > 0) {
-      const char* s16 = src + (size_t)(unsigned)cur.blk * (kObsBlock * 4) + 16 * lane;
+template <int NARR, int AHEAD>
+struct SwStream {
+  static constexpr unsigned kStage = (NARR == 5 ? kSwStageD : kSwStageJ) * 4, kRing = (AHEAD + 2) * kStage;
+  const char* src;        // this lane's 16-byte piece of the next block to request
+  int left;               // blocks not yet requested
+  unsigned ring, lane12;  // shared address of the ring; 12 * lane (piece offset - observation offset)
+  unsigned fill, rd, rd_prev;  // this lane's piece of the stage to fill | its observation in the stage to read | read last
+  __device__ __forceinline__ void request(int lane) {
+    if (left > 0) {
       if (NARR == 5) {
-        cp_async16(dst, s16);
-        if (lane < 8) cp_async16(dst + 512, s16 + 512);
+        cp_async16(fill, src);
+        if (lane < 8) cp_async16(fill + 512, src + 512);
       } else {
-        if (lane < 24) cp_async16(dst, s16);
+        if (lane < 24) cp_async16(fill, src);
       }
     }
-    if (cur.first && lane < 6) cp_async16(dst + kPoseOff, rt + (size_t)(unsigned)cur.v * 96 + 16 * lane);
-    if (lane == 0)
-      sts_s32(st + kDescOff, cur.v | (nvalid << 12) | (cur.first ? kDescFirst : 0) | (cur.rem <= 32 ? kDescLast : 0));
-    cur.next();
-  } else if (lane == 0) {
-    sts_s32(st + kDescOff, -1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    src += kObsBlock * 4;
+    --left;
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#else
-  if (lane == 0) {
-    const unsigned bar = st + kBarOff;
-    if (cur.ok) {
-      const int nvalid = min(32, cur.rem);  // 0 for an empty view
-      sts_s32(st + kDescOff, cur.v | (nvalid << 12) | (cur.first ? kDescFirst : 0) | (cur.rem <= 32 ? kDescLast : 0));
-      const unsigned tx = (nvalid > 0 ? kBytes : 0u) + (cur.first ? 96u : 0u);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
-      if (nvalid > 0)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st),
-                     "l"(src + (size_t)(unsigned)cur.blk * (kObsBlock * 4)), "n"(kBytes), "r"(bar)
-                     : "memory");
-      if (cur.first)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 96, [%2];" ::"r"(
-                         st + kPoseOff),
-                     "l"(rt + (size_t)(unsigned)cur.v * 96), "r"(bar)
-                     : "memory");
-    } else {
-      sts_s32(st + kDescOff, -1);
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  __device__ __forceinline__ void init(const float* obs_blk, int b0, int b1, unsigned ring_, int lane) {
+    ring = ring_;
+    lane12 = 12u * (unsigned)lane;
+    src = reinterpret_cast<const char*>(obs_blk) + (size_t)b0 * (kObsBlock * 4) + (NARR == 5 ? 0 : 256) + 16 * lane;
+    left = b1 - b0;
+    fill = ring + 16u * (unsigned)lane;
+#pragma unroll
+    for (int i = 0; i < AHEAD; ++i) {
+      request(lane);
+      fill += kStage;
     }
+    rd = ring + 4u * (unsigned)lane;
+    rd_prev = rd + (AHEAD + 1) * kStage;  // the last stage of the ring: free
   }
-  if (cur.ok) cur.next();
-#endif
-}
-
-// wait until the chunk in the stage at `st` has landed (AHEAD = chunks allowed to stay in flight)
-template <int NARR, int AHEAD>
-__device__ __forceinline__ void sw_wait(unsigned st, unsigned phase) {
-#ifdef CCG_SW_LDGSTS
-  asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
-#else
-  constexpr unsigned kBarOff = (NARR == 5 ? 160 : 96) * 4 + 96 + 8;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(st + kBarOff),
-      "r"(phase)
-      : "memory");
-#endif
-}
-
-// per-warp setup of a stage ring (mbarriers, one arrival per phase: lane 0's)
-template <int NARR>
-__device__ __forceinline__ void sw_ring_init(unsigned stages, int n_stages, int lane) {
-#ifndef CCG_SW_LDGSTS
-  constexpr unsigned kStride = (NARR == 5 ? kSwStageD : kSwStageJ) * 4, kBarOff = (NARR == 5 ? 160 : 96) * 4 + 96 + 8;
-  if (lane < n_stages)
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(stages + (unsigned)lane * kStride + kBarOff) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
-#endif
-}
+  __device__ __forceinline__ unsigned next(int lane) {
+    request(lane);
+    asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
+    __syncwarp();
+    const unsigned at = rd;
+    fill = rd_prev + lane12;
+    rd_prev = rd;
+    rd += kStage;
+    if (rd == ring + kRing + (lane12 / 3u)) rd -= kRing;
+    return at;
+  }
+};
 
 // keeps a lane-derived value in a register (ptxas otherwise rebuilds it from SR_TID at every use)
 __device__ __forceinline__ int opaque(int x) {
   asm volatile("mov.u32 %0, %0;" : "+r"(x));
   return x;
+}
+
+template <typename T>
+__device__ __forceinline__ T* opaque_ptr(T* p) {
+  unsigned long long x = reinterpret_cast<unsigned long long>(p);
+  asm volatile("mov.u64 %0, %0;" : "+l"(x));
+  return reinterpret_cast<T*>(x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -534,6 +560,10 @@ __global__ void __launch_bounds__(kStepThreads) k_intr_step(IntrDev d) {
     rt[3] = make_double2(R[6], R[7]);
     rt[4] = make_double2(R[8], t0);
     rt[5] = make_double2(t1, t2);
+    float4* rtf = reinterpret_cast<float4*>(d.rtf + (size_t)v * 12);  // the Jacobian role's copy
+    rtf[0] = make_float4((float)R[0], (float)R[1], (float)R[2], (float)R[3]);
+    rtf[1] = make_float4((float)R[4], (float)R[5], (float)R[6], (float)R[7]);
+    rtf[2] = make_float4((float)R[8], (float)t0, (float)t1, (float)t2);
   }
   // fixed-order block reduction (bit-reproducible)
 #pragma unroll
@@ -555,67 +585,95 @@ __global__ void __launch_bounds__(kStepThreads) k_intr_step(IntrDev d) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// The FP64 role over the views va, va + 1, ... < vb of the item: residuals, cost, g_u (into the
+// The FP64 role over the views [va, vb) (absolute view indices): residuals, cost, g_u (into the
 // warp's partial) and g_v (into the view blocks).  `stages` = shared address of the warp's ring.
 // ---------------------------------------------------------------------------------------------
-template <bool RES>
-__device__ __forceinline__ void sw_run_fp64(const IntrDev& d, int item_v0, unsigned vm, unsigned stages,
-                                            const double* s_k, int par, int va, int vb, int lane, double* upart,
-                                            double* __restrict__ res_out) {
+struct SwObs5 {
+  float mu, mv, X, Y, Z;
+};
+struct SwObs3 {
+  float X, Y, Z;
+};
+
+// LEAN (the Jacobian warps' share, fewer registers): one chunk at a time, the pose is loaded at the view's start.
+template <bool RES, bool LEAN>
+__device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, const double* s_k, int par, int va, int vb,
+                                            int lane, double* upart, double* __restrict__ res_out) {
   TcConst64 K;
   K.fx = s_k[0]; K.fy = s_k[1]; K.cx = s_k[2]; K.cy = s_k[3];
   K.k1 = s_k[4]; K.k2 = s_k[5]; K.p1 = s_k[6]; K.p2 = s_k[7]; K.k3 = s_k[8];
   double gu[9], cost = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) gu[i] = 0.0;
-  lane = opaque(lane);
-  const char* src_lane = reinterpret_cast<const char*>(d.obs_blk);
-  const char* rt_lane = reinterpret_cast<const char*>(d.rt + (size_t)item_v0 * 12);
-  sw_ring_init<5>(stages, kSwStagesD, lane);
-  double* gv_out = d.blk[par ^ 1] + (size_t)item_v0 * kBlk + 21 + lane;
-  SwCursor<1> cur;
-  cur.init(vm, va, vb);
+  if (va < vb) {
+    lane = opaque(lane);
+    const int2* vmeta = opaque_ptr(d.vmeta);
+    const double2* rt = reinterpret_cast<const double2*>(opaque_ptr(d.rt));
+    double* gv_out = opaque_ptr(d.blk[par ^ 1] + 21 + lane);
+    SwStream<5, kSwAheadD> strm;
+    strm.init(d.obs_blk, vmeta[va].x, vmeta[vb].x, (unsigned)opaque((int)stages), lane);
+    // the lane keeps the observations of the next two chunks of its stream in registers (o0: next, o1: the one
+    // after): the shared-memory latency of a chunk hides behind the arithmetic of the chunks before it
+    auto load = [&]() -> SwObs5 {
+      const unsigned a = strm.next(lane);
+      SwObs5 o;
+      o.mu = lds_f32(a); o.mv = lds_f32(a + 128); o.X = lds_f32(a + 256); o.Y = lds_f32(a + 384); o.Z = lds_f32(a + 512);
+      return o;
+    };
+    SwObs5 o0 = load(), o1 = load();
+    double2 pn[6];
+    if (!LEAN) {
 #pragma unroll
-  for (int i = 0; i <= kSwAheadD; ++i) sw_issue<5, 1>(src_lane, rt_lane, stages + i * (kSwStageD * 4), cur, lane);
-  double R[9], t[3], gv[6];
+      for (int i = 0; i < 6; ++i) pn[i] = __ldg(rt + (size_t)va * 6 + i);
+    }
+    int n_next = vmeta[va].y;
+    for (int v = va; v < vb; ++v) {
+      if (LEAN) {
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = 0.0;
+        for (int i = 0; i < 6; ++i) pn[i] = __ldg(rt + (size_t)v * 6 + i);
+      }
+      const double R[9] = {pn[0].x, pn[0].y, pn[1].x, pn[1].y, pn[2].x, pn[2].y, pn[3].x, pn[3].y, pn[4].x};
+      const double t[3] = {pn[4].y, pn[5].x, pn[5].y};
+      const int n = n_next;
+      {
+        // next view's pose and size, one view ahead (the last view re-reads itself)
+        const int vn = min(v + 1, vb - 1);
+        if (!LEAN) {
 #pragma unroll
-  for (int i = 0; i < 3; ++i) t[i] = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) gv[i] = 0.0;
-  const unsigned ring_end = stages + kSwStagesD * (kSwStageD * 4);
-  unsigned st = stages, st_prev = ring_end - kSwStageD * 4;  // stage being consumed / consumed one iteration ago
-  const unsigned lane4 = 4u * (unsigned)lane;
-  unsigned phase = 0;  // parity of the ring pass (mbarrier phase of the stage being consumed)
-  int chunk = 0;       // chunk index inside the view (residual output only)
-  for (;;) {
-    sw_wait<5, kSwAheadD>(st, phase);
-    __syncwarp();  // a lane reads what other lanes copied; the previous stage is no longer being read
-    const int desc = lds_s32(st + 184 * 4);
-    // refill the stage consumed one iteration ago (the ring has one stage more than chunks in flight)
-    sw_issue<5, 1>(src_lane, rt_lane, st_prev, cur, lane);
-    if (desc < 0) break;
-    const int nvalid = (desc >> 12) & 63;
-    if (desc & kDescFirst) {
-      const double2 a = lds_v2f64(st + 640), b = lds_v2f64(st + 656), c = lds_v2f64(st + 672),
-                    e = lds_v2f64(st + 688), f = lds_v2f64(st + 704), h = lds_v2f64(st + 720);
-      R[0] = a.x; R[1] = a.y; R[2] = b.x; R[3] = b.y; R[4] = c.x; R[5] = c.y;
-      R[6] = e.x; R[7] = e.y; R[8] = f.x; t[0] = f.y; t[1] = h.x; t[2] = h.y;
+          for (int i = 0; i < 6; ++i) pn[i] = __ldg(rt + (size_t)vn * 6 + i);
+        }
+        n_next = vmeta[vn].y;
+      }
+      double gv[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) gv[i] = 0.0;
-      chunk = 0;
-    }
-    if (nvalid > 0) {
-      const unsigned a = st + lane4;
-      const float mu = lds_f32(a), mv = lds_f32(a + 128), X = lds_f32(a + 256), Y = lds_f32(a + 384),
-                  Z = lds_f32(a + 512);
       double* res = nullptr;
-      if (RES) res = res_out + 2 * (d.view_off[item_v0 + (desc & 4095)] - d.obs_base + 32 * chunk + lane);
-      tc_fp64_observation<RES>(K, R, t, mu, mv, X, Y, Z, lane < nvalid, gu, gv, cost, res);
-    }
-    ++chunk;
-    if (desc & kDescLast) {
+      if (RES) res = res_out + 2 * (d.view_off[v] - d.obs_base + lane);
+      int c = n >> 5;  // full chunks: no masking
+      if (kSwD2 && !LEAN) {
+        for (; c >= 2; c -= 2) {
+          // two chunks at a time: two independent chains per lane
+          const SwObs5 a = o0, b = o1;
+          o0 = load();
+          o1 = load();
+          const float mu2[2] = {a.mu, b.mu}, mv2[2] = {a.mv, b.mv}, X2[2] = {a.X, b.X}, Y2[2] = {a.Y, b.Y}, Z2[2] = {a.Z, b.Z};
+          tc_fp64_observations<RES, 2>(K, R, t, mu2, mv2, X2, Y2, Z2, gu, gv, cost, res);
+          if (RES) res += 128;
+        }
+      }
+      for (; c >= 1; --c) {
+        const SwObs5 a = o0;
+        o0 = o1;
+        o1 = load();
+        tc_fp64_observation<RES, false>(K, R, t, a.mu, a.mv, a.X, a.Y, a.Z, true, gu, gv, cost, res);
+        if (RES) res += 64;
+      }
+      if (n & 31) {
+        const SwObs5 a = o0;
+        o0 = o1;
+        o1 = load();
+        tc_fp64_observation<RES, true>(K, R, t, a.mu, a.mv, a.X, a.Y, a.Z, lane < (n & 31), gu, gv, cost, res);
+      }
       // per-view gradient: reduce over lanes, fix up the rotation part, store
       double tmp[8];
 #pragma unroll
@@ -630,16 +688,10 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, int item_v0, unsig
       if (lane == 0) out = 2.0 * (r - (t[1] * sw2 - t[2] * sw1));
       if (lane == 1) out = 2.0 * (r - (t[2] * sw0 - t[0] * sw2));
       if (lane == 2) out = 2.0 * (r - (t[0] * sw1 - t[1] * sw0));
-      if (lane < 6) gv_out[(size_t)(desc & 4095) * kBlk] = out;
+      if (lane < 6) gv_out[(size_t)v * kBlk] = out;
     }
-    st_prev = st;
-    st += kSwStageD * 4;
-    if (st == ring_end) {
-      st = stages;
-      phase ^= 1u;
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   // lane-private sums -> the warp's partial: [0] sum r^2 | [16..24] g_u
   double tmp[16];
 #pragma unroll
@@ -654,84 +706,97 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, int item_v0, unsig
 }
 
 // ---------------------------------------------------------------------------------------------
-// The Jacobian + tensor role over the views va, va + kSwJPD, ... < vb of the item: V, W (into the
-// view blocks) and U (into the warp's partial).  `stages`, `tiles` = shared addresses.
+// The Jacobian + tensor role over the views [va, vb): V, W (into the view blocks) and U (into the
+// warp's partial).  `stages`, `tile` = shared addresses.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sw_run_jac(const IntrDev& d, int item_v0, unsigned vm, unsigned stages, unsigned tiles,
-                                           const double* s_k, int par, int va, int vb, int lane, double* upart) {
+__device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, unsigned tile, const double* s_k, int par,
+                                           int va, int vb, int lane, double* upart) {
+  if (va >= vb) return;
+  lane = opaque(lane);
+  tile = (unsigned)opaque((int)tile);
   const int g = lane >> 2, tig = lane & 3;
   TcConst32 K;
   K.fx = (float)s_k[0]; K.fy = (float)s_k[1];
   K.k1 = (float)s_k[4]; K.k2 = (float)s_k[5]; K.p1 = (float)s_k[6]; K.p2 = (float)s_k[7]; K.k3 = (float)s_k[8];
-  lane = opaque(lane);
-  const char* src_lane = reinterpret_cast<const char*>(d.obs_blk) + 256;
-  const char* rt_lane = reinterpret_cast<const char*>(d.rt + (size_t)item_v0 * 12);
-  sw_ring_init<3>(stages, kSwStagesJ, lane);
-  double* blk0 = d.blk[par ^ 1] + (size_t)item_v0 * kBlk;
-  SwCursor<kSwJPD> cur;
-  cur.init(vm, va, vb);
+  const int2* vmeta = opaque_ptr(d.vmeta);
+  const float4* rtf = reinterpret_cast<const float4*>(opaque_ptr(d.rtf));
+  double* blk0 = opaque_ptr(d.blk[par ^ 1]);
+  SwStream<3, kSwAheadJ> strm;
+  strm.init(d.obs_blk, vmeta[va].x, vmeta[vb].x, (unsigned)opaque((int)stages), lane);
+  auto load = [&]() -> SwObs3 {
+    const unsigned a = strm.next(lane);
+    SwObs3 o;
+    o.X = lds_f32(a); o.Y = lds_f32(a + 128); o.Z = lds_f32(a + 256);
+    return o;
+  };
+  SwObs3 o0 = load(), o1 = load();
+  const unsigned row_u = tile + (unsigned)lane * (kTcRow * 4);            // this lane's u row (v row: + 32 rows)
+  const unsigned frag = tile + (unsigned)(2 * tig * kTcRow + 2 * g) * 4;  // this lane's fragment of k-step 0
+  float4 pn[3];
 #pragma unroll
-  for (int i = 0; i <= kSwAheadJ; ++i) sw_issue<3, kSwJPD>(src_lane, rt_lane, stages + i * (kSwStageJ * 4), cur, lane);
-  float Rf[9], tf[3];
+  for (int i = 0; i < 3; ++i) pn[i] = __ldg(rtf + (size_t)va * 3 + i);
+  int n_next = vmeta[va].y;
+  for (int v = va; v < vb; ++v) {
+    const float Rf[9] = {pn[0].x, pn[0].y, pn[0].z, pn[0].w, pn[1].x, pn[1].y, pn[1].z, pn[1].w, pn[2].x};
+    const float tf[3] = {pn[2].y, pn[2].z, pn[2].w};
+    const int n = n_next;
+    {
+      const int vn = min(v + 1, vb - 1);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) Rf[i] = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) tf[i] = 0.0f;
-  // product columns 0..7 (c0*) and 8..15 (c1*), two accumulator sets each
-  float c0a[4] = {0.f, 0.f, 0.f, 0.f}, c0b[4] = {0.f, 0.f, 0.f, 0.f};
-  float c1a[4] = {0.f, 0.f, 0.f, 0.f}, c1b[4] = {0.f, 0.f, 0.f, 0.f};
-  const unsigned ring_end = stages + kSwStagesJ * (kSwStageJ * 4);
-  unsigned st = stages, st_prev = ring_end - kSwStageJ * 4;
-  const unsigned lane4 = 4u * (unsigned)lane;
-  const unsigned row_u = tiles + (unsigned)lane * (kTcRow * 4);               // this lane's u row (v row: + 32 rows)
-  const unsigned frag = tiles + (unsigned)(2 * tig * kTcRow + 2 * g) * 4;  // this lane's fragment of k-step 0
-  unsigned tsel = 0;   // byte offset of the tile in use (kSwTiles == 2: alternates)
-  unsigned phase = 0;  // parity of the ring pass (mbarrier phase of the stage being consumed)
-  for (;;) {
-    sw_wait<3, kSwAheadJ>(st, phase);
-    __syncwarp();  // stage visible to every lane; the tile written two chunks ago has been read
-    const int desc = lds_s32(st + 120 * 4);
-    sw_issue<3, kSwJPD>(src_lane, rt_lane, st_prev, cur, lane);
-    if (desc < 0) break;
-    const int nvalid = (desc >> 12) & 63;
-    if (desc & kDescFirst) {
-      const double2 a = lds_v2f64(st + 384), b = lds_v2f64(st + 400), c = lds_v2f64(st + 416),
-                    e = lds_v2f64(st + 432), f = lds_v2f64(st + 448), h = lds_v2f64(st + 464);
-      Rf[0] = (float)a.x; Rf[1] = (float)a.y; Rf[2] = (float)b.x; Rf[3] = (float)b.y; Rf[4] = (float)c.x;
-      Rf[5] = (float)c.y; Rf[6] = (float)e.x; Rf[7] = (float)e.y; Rf[8] = (float)f.x;
-      tf[0] = (float)f.y; tf[1] = (float)h.x; tf[2] = (float)h.y;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) c0a[i] = c0b[i] = c1a[i] = c1b[i] = 0.0f;
+      for (int i = 0; i < 3; ++i) pn[i] = __ldg(rtf + (size_t)vn * 3 + i);
+      n_next = vmeta[vn].y;
     }
-    if (nvalid > 0) {
-      const unsigned a = st + lane4;
-      const float X = lds_f32(a), Y = lds_f32(a + 128), Z = lds_f32(a + 256);
-      float4 ur[4], vr[4];
-      tc_fp32_rows(K, Rf, tf, X, Y, Z, lane < nvalid, ur, vr);
-      tc_store_rows(row_u + tsel, ur, vr);
-      __syncwarp();
-      if (nvalid == 32) tc_contract<true>(frag + tsel, 32, c0a, c0b, c1a, c1b);
-      else tc_contract<false>(frag + tsel, nvalid, c0a, c0b, c1a, c1b);
-      if (kSwTiles > 1) tsel ^= kTcTile * 4;
-    }
-    if (desc & kDescLast) {
-      // per-view epilogue: V, W blocks and the view's contribution to U
-      double* blk = blk0 + (size_t)(desc & 4095) * kBlk;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int nt = i >> 2, e = i & 3;
-        const int row = g + ((e & 2) ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
-        const float val = nt == 0 ? c0a[e] + c0b[e] : c1a[e] + c1b[e];
-        const int bs = tc_blk_slot(row, col), us = tc_u_slot(row, col);
-        if (bs >= 0) blk[bs] = (double)val;
-        if (us >= 0) upart[us] += (double)val;  // one owner lane per slot within the warp
+    // product columns 0..7 (c0*) and 8..15 (c1*), two accumulator sets each
+    float c0a[4] = {0.f, 0.f, 0.f, 0.f}, c0b[4] = {0.f, 0.f, 0.f, 0.f};
+    float c1a[4] = {0.f, 0.f, 0.f, 0.f}, c1b[4] = {0.f, 0.f, 0.f, 0.f};
+    // per chunk: rows -> tile -> contraction.  The __syncwarp inside load() orders the previous chunk's tile
+    // reads before this chunk's tile writes.
+    int c = n >> 5;  // full chunks: no masking
+    if (kSwJ2) {
+      for (; c >= 2; c -= 2) {
+        const SwObs3 a = o0, b = o1;
+        o0 = load();
+        o1 = load();
+        float4 ur[4], vr[4];
+        tc_fp32_rows<false>(K, Rf, tf, a.X, a.Y, a.Z, true, ur, vr);
+        tc_store_rows(row_u, ur, vr);
+        tc_fp32_rows<false>(K, Rf, tf, b.X, b.Y, b.Z, true, ur, vr);
+        tc_store_rows(row_u + kTcTile * 4, ur, vr);
+        __syncwarp();
+        tc_contract<true>(frag, 32, c0a, c0b, c1a, c1b);
+        tc_contract<true>(frag + kTcTile * 4, 32, c0a, c0b, c1a, c1b);
       }
     }
-    st_prev = st;
-    st += kSwStageJ * 4;
-    if (st == ring_end) {
-      st = stages;
-      phase ^= 1u;
+    for (; c >= 1; --c) {
+      const SwObs3 a = o0;
+      o0 = o1;
+      o1 = load();
+      float4 ur[4], vr[4];
+      tc_fp32_rows<false>(K, Rf, tf, a.X, a.Y, a.Z, true, ur, vr);
+      tc_store_rows(row_u, ur, vr);
+      __syncwarp();
+      tc_contract<true>(frag, 32, c0a, c0b, c1a, c1b);
+    }
+    if (n & 31) {
+      const SwObs3 a = o0;
+      o0 = o1;
+      o1 = load();
+      float4 ur[4], vr[4];
+      tc_fp32_rows<true>(K, Rf, tf, a.X, a.Y, a.Z, lane < (n & 31), ur, vr);
+      tc_store_rows(row_u, ur, vr);
+      __syncwarp();
+      tc_contract<false>(frag, n & 31, c0a, c0b, c1a, c1b);
+    }
+    // per-view epilogue: V, W blocks and the view's contribution to U
+    double* blk = blk0 + (size_t)v * kBlk;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int nt = i >> 2, e = i & 3;
+      const int row = g + ((e & 2) ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
+      const float val = nt == 0 ? c0a[e] + c0b[e] : c1a[e] + c1b[e];
+      const int bs = tc_blk_slot(row, col), us = tc_u_slot(row, col);
+      if (bs >= 0) blk[bs] = (double)val;
+      if (us >= 0) upart[us] += (double)val;  // one owner lane per slot within the warp
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -744,10 +809,9 @@ template <bool RES>
 __global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, double* __restrict__ res_out) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   double(*s_part)[kSweepPart] = reinterpret_cast<double(*)[kSweepPart]>(s_dyn);
-  int2* s_vm = reinterpret_cast<int2*>(s_dyn + sizeof(double) * kSwWarps * kSweepPart);
-  float* s_stage_d = reinterpret_cast<float*>(s_vm + kSwMaxViews);
-  float* s_stage_j = s_stage_d + kSwD * kSwStagesD * kSwStageD;
-  float* s_tiles = s_stage_j + kSwJ * kSwStagesJ * kSwStageJ;
+  float* s_stage_d = reinterpret_cast<float*>(s_dyn + sizeof(double) * kSwWarps * kSweepPart);
+  float* s_stage_j = s_stage_d + kSwPairs * kSwStagesD * kSwStageD;
+  float* s_tiles = s_stage_j + kSwPairs * kSwStagesJ * kSwStageJ;
   __shared__ double s_k[9];
   __shared__ int s_meta[2];
   const WorkItem it = d.items[blockIdx.x];
@@ -759,28 +823,41 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, doub
   __syncthreads();
   if (!s_meta[1]) return;
   const int par = s_meta[0];
-  const int nv = it.v1 - it.v0;  // <= kSwMaxViews (build_problem)
   if (threadIdx.x < 9) s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
   for (int i = threadIdx.x; i < kSwWarps * kSweepPart; i += kSwThreads) (&s_part[0][0])[i] = 0.0;
-  for (int i = threadIdx.x; i < nv; i += kSwThreads) s_vm[i] = d.vmeta[it.v0 + i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* upart = s_part[warp];
-  const unsigned vm = smem_u32(s_vm);
-  if (warp >= kSwJ) {
+  // pair p (Jacobian warp p, FP64 warp kSwPairs + p, same SM sub-partition) owns the p-th part of the item's views
+  const int pair = warp & (kSwPairs - 1), nv = it.v1 - it.v0;
+  const int va = it.v0 + (int)((int64_t)nv * pair / kSwPairs), vb = it.v0 + (int)((int64_t)nv * (pair + 1) / kSwPairs);
+  const int vsplit = va + ((vb - va) * (64 - kSwTail) + 32) / 64;  // FP64 role: [va, vsplit) the FP64 warp, the rest its partner
+#ifdef CCG_SW_D_FIRST  // experiment: which warp ids the issue arbiter prefers
+  if (warp < kSwPairs) {
+#else
+  if (warp >= kSwPairs) {
+#endif
     // =========================== FP64 role ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSwRegD));
-    const int grp = warp - kSwJ;
-    const int va = (int)((int64_t)nv * grp / kSwD), vb = (int)((int64_t)nv * (grp + 1) / kSwD);
-    sw_run_fp64<RES>(d, it.v0, vm, smem_u32(s_stage_d + grp * kSwStagesD * kSwStageD), s_k, par, va, vb, lane, upart,
-                     res_out);
+    if (kSwRegD > kSwRegLaunch) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSwRegD));
+#ifndef CCG_SW_ONLY_J  // timing experiments: one role alone (results are then incomplete)
+    sw_run_fp64<RES, false>(d, smem_u32(s_stage_d + pair * kSwStagesD * kSwStageD), s_k, par, va, vsplit, lane, upart,
+                            res_out);
+#endif
   } else {
     // =========================== Jacobian + tensor role ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSwRegJ));
-    const int grp = warp % kSwD, j = warp / kSwD;
-    const int va = (int)((int64_t)nv * grp / kSwD), vb = (int)((int64_t)nv * (grp + 1) / kSwD);
-    sw_run_jac(d, it.v0, vm, smem_u32(s_stage_j + warp * kSwStagesJ * kSwStageJ),
-               smem_u32(s_tiles + warp * kSwTiles * kTcTile), s_k, par, va + j, vb, lane, upart);
+    if (kSwRegJ < kSwRegLaunch) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSwRegJ));
+#ifndef CCG_SW_ONLY_D
+    sw_run_jac(d, smem_u32(s_stage_j + pair * kSwStagesJ * kSwStageJ), smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k, par, va, vb,
+               lane, upart);
+#endif
+#ifndef CCG_SW_ONLY_J
+    // the tail of the pair's FP64 work; the ring lives in the tile(s), free by now (every lane is past its last
+    // tile read: sw_run_fp64 synchronises the warp before the first ring write lands)
+    if (kSwTail > 0) {
+      __syncwarp();
+      sw_run_fp64<RES, true>(d, smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k, par, vsplit, vb, lane, upart, res_out);
+    }
+#endif
   }
   __syncthreads();
   if (threadIdx.x < kSweepPart) {

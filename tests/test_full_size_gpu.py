@@ -1,13 +1,14 @@
-"""BASELINE.json's full sizes on the GPU, checked through size-independent properties (the oracle
-needs minutes at these sizes): recovery of the generator's ground truth, the noise-level RMS, a
-vanishing gradient, additivity of the normal equations over a partition of the views, run-to-run
-bit reproducibility, and oracle parity on a random sample of the batch."""
+"""BASELINE.json's full sizes on the GPU: oracle parity at the two sizes `north_star` targets (C5:
+100,000 views x 400 points against the OpenMP oracle, C3: 4 cameras x 1,000 frames x 187 points with
+Huber active), plus size-independent properties: recovery of the generator's ground truth, the
+noise-level RMS, a vanishing gradient, additivity of the normal equations over a partition of the
+views, run-to-run bit reproducibility, and oracle parity on a random sample of the C4 batch."""
 import numpy as np
 import pytest
 
 import oracle
-from camera_calibrator_b200 import synth
-from helpers import TOL_PARAM, TOL_RMS, rel_err
+from camera_calibrator_b200 import rig_api, synth
+from helpers import TOL_PARAM, TOL_RMS, quat_to_rot, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -84,3 +85,43 @@ def test_c4_full_batch_properties(ctx):
         ref = oracle.intrinsics_solve(x.u, x.v, x.X, x.Y, x.Z, x.view_offsets, st[b][0], st[b][1], st[b][2])
         assert rel_err(gi[b], ref[0], floor=1e-300) <= TOL_PARAM, b
         assert abs(reps[b]["rms"] - ref[3]["rms"]) <= TOL_RMS, b
+
+
+def test_c5_full_size_matches_oracle(ctx):
+    """configs[4] at full size against the oracle (reference src/calibrator.cpp:221-336 restated; all host
+    threads, about half a minute): intrinsics to 1e-6 relative, final RMS to 1e-9, every pose to 1e-6."""
+    d = synth.planar_views(100000, 400, seed=0)
+    intr0, q0, t0 = synth.perturbed_start(d)
+    got = ctx.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr0, q0, t0)
+    ref = oracle.intrinsics_solve(d.u, d.v, d.X, d.Y, d.Z, d.view_offsets, intr0, q0, t0)
+    gi, gq, gt, grep = got
+    ri, rq, rt, rrep = ref
+    assert grep["termination"] in (1, 2, 3) and rrep["termination"] in (1, 2, 3)
+    assert rel_err(gi, ri, floor=1e-300) <= TOL_PARAM, (gi, ri)
+    assert abs(grep["rms"] - rrep["rms"]) <= TOL_RMS
+    assert np.max(np.abs(quat_to_rot(gq) - quat_to_rot(rq))) <= TOL_PARAM
+    assert rel_err(gt, rt, floor=1e-3) <= TOL_PARAM
+    assert grep["sweeps"] == rrep["sweeps"]  # the same LM path, not only the same minimum
+
+
+def test_c3_full_size_matches_oracle(ctx):
+    """configs[2] at full size: 4 cameras x 1,000 frames x 187 points = 748,000 observations, 5 % gross
+    outliers so the Huber loss is active (reference src/extrinsics_calibrator.cpp:86-257 restated)."""
+    s = synth.rig_scene(n_cams=4, n_frames=1000, grid=(17, 11), seed=0, outlier_fraction=0.05)
+    assert s.u.size == 4 * 1000 * 187
+    args = (s.u, s.v, s.obs_cam, s.obs_point, s.frame_offsets, s.Xw)
+    got = rig_api.rig_solve(ctx, *args, s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    ref = oracle.rig_solve(*args, s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    gqc, gtc, gqf, gtf, gcost, grep = got
+    rqc, rtc, rqf, rtf, rcost, rrep = ref
+    assert grep["termination"] in (1, 2, 3)
+    assert np.max(np.abs(quat_to_rot(gqc) - quat_to_rot(rqc))) <= TOL_PARAM
+    assert np.max(np.abs(quat_to_rot(gqf) - quat_to_rot(rqf))) <= TOL_PARAM
+    assert rel_err(gtc[1:], rtc[1:], floor=1e-3) <= TOL_PARAM
+    assert rel_err(gtf, rtf, floor=1e-3) <= TOL_PARAM
+    assert abs(grep["rms"] - rrep["rms"]) <= TOL_RMS
+    assert np.array_equal(gqc[0], s.q_c[0]) and np.array_equal(gtc[0], s.t_c[0])  # frozen camera, bit-exact
+    assert gcost.shape == rcost.shape == (748000,)
+    assert np.max(np.abs(gcost - rcost)) <= 1e-9 * np.max(rcost)
+    huber = float(np.float32(3.0) / np.float32(500.0))
+    assert np.count_nonzero(rcost > 0.5 * huber * huber) > 10000  # the linear zone of the loss is populated
