@@ -62,19 +62,21 @@ static_assert(kSwRegD >= kSwRegLaunch && kSwRegD <= 256 && kSwRegJ % 8 == 0, "re
 #endif
 constexpr int kSwAheadD = CCG_SW_AHEAD_D, kSwStagesD = kSwAheadD + 2;  // blocks in flight / ring size
 constexpr int kSwAheadJ = CCG_SW_AHEAD_J, kSwStagesJ = kSwAheadJ + 2;
-// chunks a warp works on at a time: 2 = two independent dependency chains per lane (the FP64 pipe needs ~4
-// chains per SM sub-partition to be busy: DFMA latency 8 cycles, issue interval 2.2, tools/ubench_dfma_latency.cu)
+// chunks a warp works on at a time (2 = two chunks per loop trip).  Measured on C5: no effect for either role -
+// ptxas serialises the two chains under the register budget, and the kernel is bound by the pipe FP64 and
+// legacy tensor instructions share, not by dependent-issue latency (profiles/r02_sweep_experiments.md).
 #ifndef CCG_SW_D2
-#define CCG_SW_D2 1
+#define CCG_SW_D2 0
 #endif
 #ifndef CCG_SW_J2
 #define CCG_SW_J2 1
 #endif
 constexpr bool kSwD2 = CCG_SW_D2 != 0, kSwJ2 = CCG_SW_J2 != 0;
-// The FP64 role is the slower one when both run, so a Jacobian warp also runs the FP64 role on the last
-// kSwTail / 64 of its pair's views once its own work is done (static split: sums stay bit-reproducible).
+// A Jacobian warp can also run the FP64 role on the last kSwTail / 64 of its pair's views once its own work is
+// done (static split: sums stay bit-reproducible).  Measured on C5: 0 .. 22 / 64 all within 2 % - the FP64 role is
+// bound by its pipe, not by the number of warps that feed it - so it is off by default.
 #ifndef CCG_SW_TAIL
-#define CCG_SW_TAIL 12
+#define CCG_SW_TAIL 0
 #endif
 constexpr int kSwTail = CCG_SW_TAIL;
 constexpr int kSwTiles = kSwJ2 ? 2 : 1;  // Jacobian-row tiles per Jacobian warp
@@ -417,6 +419,9 @@ __device__ __forceinline__ void tc_store_rows(unsigned row_u, const float4 (&ur)
 template <bool FULL>
 __device__ __forceinline__ void tc_contract(unsigned frag, int nvalid, float (&c0a)[4], float (&c0b)[4],
                                             float (&c1a)[4], float (&c1b)[4]) {
+#ifdef CCG_SW_NO_MMA  // timing experiment: no contraction (results are then wrong)
+  return;
+#endif
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     if (FULL || 8 * (s & 3) < nvalid) {
@@ -424,6 +429,10 @@ __device__ __forceinline__ void tc_contract(unsigned frag, int nvalid, float (&c
       const float2 hi = lds_v2f32(frag + (8 * s + 1) * kTcRow * 4);
       const unsigned a0 = __float_as_uint(lo.x), a1 = __float_as_uint(lo.y);
       const unsigned a2 = __float_as_uint(hi.x), a3 = __float_as_uint(hi.y);
+#ifdef CCG_SW_NO_HMMA  // timing experiment: fragment loads without the MMAs
+      c0a[0] += __uint_as_float(a0 ^ a1 ^ a2 ^ a3);
+      continue;
+#endif
       if (s & 1) {
         mma_tf32_16x8x8(c0b, a0, a1, a2, a3, a0, a2);
         mma_tf32_16x8x8(c1b, a0, a1, a2, a3, a1, a3);
@@ -850,7 +859,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, doub
     sw_run_jac(d, smem_u32(s_stage_j + pair * kSwStagesJ * kSwStageJ), smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k, par, va, vb,
                lane, upart);
 #endif
-#ifndef CCG_SW_ONLY_J
+#if !defined(CCG_SW_ONLY_J) || defined(CCG_SW_TAIL_ANYWAY)
     // the tail of the pair's FP64 work; the ring lives in the tile(s), free by now (every lane is past its last
     // tile read: sw_run_fp64 synchronises the warp before the first ring write lands)
     if (kSwTail > 0) {
