@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstddef>
+
 #include <string>
 #include <vector>
 
@@ -211,11 +213,13 @@ __device__ inline void lm_reject(LmState& s, const LmParams& P, int* n_done) {
 // Step-acceptance logic after a sweep evaluated the candidate.  cost_c is the
 // candidate cost, gTd/dDd the full-model terms.  Returns true when the
 // candidate becomes the current point (the caller then flips `par` data).
+// `hist` = the trace ring the row goes to: s.hist, or the one in global memory when s is a staged copy of the
+// state's head (everything before hist) in shared memory.
 __device__ inline bool lm_decide(LmState& s, const LmParams& P, double cost_c, double gTd,
-                                 double dDd, int* n_done) {
+                                 double dDd, int* n_done, double (*hist)[6]) {
   bool accept = false;
   s.sweeps++;
-  double* h = s.hist[s.n_hist % kHist];
+  double* h = hist[s.n_hist % kHist];
   s.n_hist++;
   h[0] = s.cost;
   h[1] = cost_c;
@@ -268,6 +272,58 @@ __device__ inline bool lm_decide(LmState& s, const LmParams& P, double cost_c, d
   }
   if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, n_done, true);
   return accept;
+}
+
+__device__ inline bool lm_decide(LmState& s, const LmParams& P, double cost_c, double gTd, double dDd, int* n_done) {
+  return lm_decide(s, P, cost_c, gTd, dDd, n_done, s.hist);
+}
+
+// 8-byte words of LmState before the trace ring: what a CTA stages in shared memory to run the state machine
+constexpr int kLmHeadWords = (int)(offsetof(LmState, hist) / 8);
+static_assert(offsetof(LmState, hist) % 8 == 0, "LmState head");
+
+// Cholesky solve of an N x N SPD system by ONE thread, entirely in registers (fully unrolled; N small and known
+// at compile time): S row-major in (shared) memory, lower triangle read; b in, solution out.  One rsqrt per pivot,
+// no divisions.  Returns false when a pivot is not positive.
+template <int N>
+__device__ __forceinline__ bool chol_solve_reg(const double* S, double (&b)[N]) {
+  double L[N][N], dinv[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) L[i][j] = S[i * N + j];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double dj = L[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) dj = fma(-L[j][k], L[j][k], dj);
+    ok = ok && (dj > 0.0) && isfinite(dj);
+    const double r = rsqrt(dj);
+    dinv[j] = r;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      double v = L[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-L[i][k], L[j][k], v);
+      L[i][j] = v * r;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v = fma(-L[i][k], b[k], v);
+    b[i] = v * dinv[i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) v = fma(-L[k][i], b[k], v);
+    b[i] = v * dinv[i];
+  }
+  return ok;
 }
 
 // Called by all threads of a CTA with at least kPeerVals threads; s_vals[0..64) in shared memory is

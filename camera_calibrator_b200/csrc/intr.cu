@@ -35,6 +35,7 @@ constexpr int kYz = 72;         // per-view elimination record: Y 54 | z 6 | gv 
 constexpr int kPose = 8;        // q4 t3 pad
 constexpr int kSweepPart = 64;  // per-item sweep partial (doubles)
 constexpr int kSchurPart = 64;  // per-item elimination partial: S upper 45 | rhs 9 | g'D^-1g | fails
+constexpr int kRedSeg = 8;      // segments of the fixed-order reduction of the partials (block_reduce_items)
 constexpr int kWarps = 8;       // warps per CTA (4 view pairs in the sweep, 8 views in the elimination)
 
 // sweep partial layout
@@ -66,7 +67,6 @@ struct IntrDev {
   double* yz;
   double* rt;         // candidate pose as rotation matrix + translation, 12 doubles per view (default sweep, FP64 role)
   float* rtf;         // the same in float32 (Jacobian role)
-  double* step_part;  // g'd, d'Dd partials of the candidate-pose kernel: [item * schur_split + sub][2]
   double* sweep_part;
   double* schur_part;
   double* red_sweep;  // [B][64]
@@ -352,19 +352,18 @@ namespace ccg {
 // --------------------------------------------------------------------------
 // pose elimination, one THREAD per view: Cholesky of V + lambda D, T = L^-1 [W g_v],
 // Y = L^-T T (stored for the back-substitution), contributions T'T and T't_g to the
-// reduced system.  A warp stages 32 consecutive view blocks through shared memory
-// (coalesced global reads/writes, conflict-free odd stride), each lane eliminates
-// one view, and the 56 reduced-system terms are summed across lanes with the
-// transposing shuffle reduction.
+// reduced system.  A lane reads its view's block (672 B, contiguous) straight into registers with
+// 16-byte loads - all 41 in flight at once, the neighbouring half of every 32-byte sector is an L1
+// hit for the next load - and writes the record the same way; the 56 reduced-system terms are summed
+// across lanes with the transposing shuffle reduction.
 // --------------------------------------------------------------------------
 constexpr int kSchurWarps = 2;
-constexpr int kStage = 85;  // odd stride (doubles) of one staged view block: conflict-free LDS.64
+static_assert(kBlk % 2 == 0 && kYz % 2 == 0, "16-byte rows");
 
 // packed index of (j,k), j <= k, in the 9x9 upper triangle
 __host__ __device__ constexpr int up9(int j, int k) { return j * 9 - j * (j - 1) / 2 + (k - j); }
 
 __global__ void __launch_bounds__(kSchurWarps * 32) k_intr_schur(IntrDev d, LmParams P) {
-  __shared__ double s_stage[kSchurWarps][32 * kStage];
   __shared__ double s_part[kSchurWarps][kSchurPart];
   __shared__ int s_meta[2];
   __shared__ double s_lambda;
@@ -388,117 +387,132 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_intr_schur(IntrDev d, LmPa
   const int par = s_meta[0];
   const double lambda = s_lambda;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* stage = s_stage[warp];
   double racc0 = 0.0, racc1 = 0.0;  // lane L: reduced-system terms L and 32+L
   for (int64_t base = it.v0 + warp * 32; base < it.v1; base += kSchurWarps * 32) {
     const int nv = (int)min((int64_t)32, it.v1 - base);
-    const double* blk = d.blk[par] + (size_t)base * kBlk;
-    for (int vi = 0; vi < nv; ++vi)
+    const bool has = lane < nv;
+    // (an idle lane computes on a harmless unit block and contributes zeros)
+    double s[kBlk];
 #pragma unroll
-      for (int e = lane; e < 81; e += 32) stage[vi * kStage + e] = blk[vi * kBlk + e];
-    __syncwarp();
-    double vals[64];
+    for (int i = 0; i < kBlk; ++i) s[i] = 0.0;
+    s[0] = s[6] = s[11] = s[15] = s[18] = s[20] = 1.0;
+    if (has) {
+      const double2* src = reinterpret_cast<const double2*>(d.blk[par] + (size_t)(base + lane) * kBlk);
 #pragma unroll
-    for (int i = 0; i < 64; ++i) vals[i] = 0.0;
-    if (lane < nv) {
-      double* s = stage + lane * kStage;
-      double A[6][6], Dv[6], tg[6];
-      {
-        int idx = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-          for (int b = a; b < 6; ++b) {
-            A[b][a] = s[idx];
-            ++idx;
-          }
+      for (int i = 0; i < 41; ++i) {
+        const double2 t = src[i];
+        s[2 * i] = t.x;
+        s[2 * i + 1] = t.y;
       }
-      double gDg = 0.0;
+    }
+    double A[6][6], Dv[6], tg[6], gv[6];
+    {
+      int idx = 0;
 #pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        tg[a] = s[21 + a];
-        Dv[a] = clampd(A[a][a], P.min_diagonal, P.max_diagonal);
-        if (A[a][a] > 0.0) gDg += tg[a] * tg[a] / A[a][a];
-        A[a][a] += lambda * Dv[a];
-      }
-      const bool ok = chol6(A);
-      double T[6][9];
+      for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int a = 0; a < 6; ++a) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) T[a][c] = s[27 + a * 4 + c];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) T[a][4 + c] = s[51 + a * 5 + c];
-      }
-      // record for the sweep prologue: g_v and D_v (the block slots are consumed by now)
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        s[60 + a] = tg[a];
-        s[66 + a] = Dv[a];
-      }
-      // forward substitution: T <- L^-1 W, tg <- L^-1 g_v
-      double inv[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) inv[i] = 1.0 / A[i][i];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int k = 0; k < i; ++k) {
-#pragma unroll
-          for (int c = 0; c < 9; ++c) T[i][c] -= A[i][k] * T[k][c];
-          tg[i] -= A[i][k] * tg[k];
+        for (int b = a; b < 6; ++b) {
+          A[b][a] = s[idx];
+          ++idx;
         }
+    }
+    double gDg = 0.0;
 #pragma unroll
-        for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
-        tg[i] *= inv[i];
+    for (int a = 0; a < 6; ++a) {
+      tg[a] = gv[a] = s[21 + a];
+      Dv[a] = clampd(A[a][a], P.min_diagonal, P.max_diagonal);
+      if (A[a][a] > 0.0) gDg += tg[a] * tg[a] / A[a][a];
+      A[a][a] += lambda * Dv[a];
+    }
+    const bool ok = chol6(A);
+    double T[6][9];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) T[a][c] = s[27 + a * 4 + c];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) T[a][4 + c] = s[51 + a * 5 + c];
+    }
+    // forward substitution: T <- L^-1 W, tg <- L^-1 g_v
+    double inv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) inv[i] = 1.0 / A[i][i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int k = 0; k < i; ++k) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) T[i][c] -= A[i][k] * T[k][c];
+        tg[i] -= A[i][k] * tg[k];
       }
-      // reduced-system terms: (W' V'^-1 W)[j][k] = T[:,j].T[:,k], (W' V'^-1 g)[j] = T[:,j].tg
+#pragma unroll
+      for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
+      tg[i] *= inv[i];
+    }
+    // reduced-system terms: (W' V'^-1 W)[j][k] = T[:,j].T[:,k] (packed upper, 45), (W' V'^-1 g)[j] = T[:,j].tg (9),
+    // g'D^-1g, failures - summed over the warp's lanes 32 terms at a time (fewer live registers)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double vals[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) vals[i] = 0.0;
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
 #pragma unroll
         for (int k = j; k < 9; ++k) {
+          const int e = up9(j, k) - 32 * half;
+          if (e >= 0 && e < 32) {
+            double acc = 0.0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc = fma(T[a][j], T[a][k], acc);
+            vals[e] = acc;
+          }
+        }
+        const int e = 45 + j - 32 * half;
+        if (e >= 0 && e < 32) {
           double acc = 0.0;
 #pragma unroll
-          for (int a = 0; a < 6; ++a) acc = fma(T[a][j], T[a][k], acc);
-          vals[up9(j, k)] = acc;
+          for (int a = 0; a < 6; ++a) acc = fma(T[a][j], tg[a], acc);
+          vals[e] = acc;
         }
-        double acc = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) acc = fma(T[a][j], tg[a], acc);
-        vals[45 + j] = acc;
       }
-      vals[54] = gDg;
-      vals[55] = ok ? 0.0 : 1.0;
-      // backward substitution: Y = L^-T T, z = L^-T tg
+      if (half == 1) {
+        vals[54 - 32] = gDg;
+        vals[55 - 32] = ok ? 0.0 : 1.0;
+      }
+      if (!has) {
 #pragma unroll
-      for (int i = 5; i >= 0; --i) {
+        for (int i = 0; i < 32; ++i) vals[i] = 0.0;
+      }
+      const double r = warp_reduce32(vals, lane);
+      if (half == 0) racc0 += r;
+      else racc1 += r;
+    }
+    // backward substitution: Y = L^-T T, z = L^-T tg
 #pragma unroll
-        for (int k = i + 1; k < 6; ++k) {
+    for (int i = 5; i >= 0; --i) {
 #pragma unroll
-          for (int c = 0; c < 9; ++c) T[i][c] -= A[k][i] * T[k][c];
-          tg[i] -= A[k][i] * tg[k];
-        }
+      for (int k = i + 1; k < 6; ++k) {
 #pragma unroll
-        for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
-        tg[i] *= inv[i];
+        for (int c = 0; c < 9; ++c) T[i][c] -= A[k][i] * T[k][c];
+        tg[i] -= A[k][i] * tg[k];
       }
 #pragma unroll
-      for (int a = 0; a < 6; ++a) {
+      for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
+      tg[i] *= inv[i];
+    }
+    if (has) {
+      // the elimination record: Y 54 | z 6 | g_v 6 | D_v 6
+      double2* dst = reinterpret_cast<double2*>(d.yz + (size_t)(base + lane) * kYz);
 #pragma unroll
-        for (int c = 0; c < 9; ++c) s[a * 9 + c] = T[a][c];
-        s[54 + a] = tg[a];
+      for (int i = 0; i < 27; ++i) dst[i] = make_double2(T[(2 * i) / 9][(2 * i) % 9], T[(2 * i + 1) / 9][(2 * i + 1) % 9]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        dst[27 + i] = make_double2(tg[2 * i], tg[2 * i + 1]);
+        dst[30 + i] = make_double2(gv[2 * i], gv[2 * i + 1]);
+        dst[33 + i] = make_double2(Dv[2 * i], Dv[2 * i + 1]);
       }
     }
-    __syncwarp();
-    double* yz = d.yz + (size_t)base * kYz;
-    for (int vi = 0; vi < nv; ++vi)
-#pragma unroll
-      for (int e = lane; e < kYz; e += 32) yz[vi * kYz + e] = stage[vi * kStage + e];
-    double out[2];
-    warp_reduce_array<64>(vals, lane, out);
-    racc0 += out[0];
-    racc1 += out[1];
-    __syncwarp();
   }
   s_part[warp][lane] = racc0;
   s_part[warp][32 + lane] = racc1;
@@ -514,19 +528,30 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_intr_schur(IntrDev d, LmPa
 // --------------------------------------------------------------------------
 // fixed-order reduction of per-item partials of one problem (blockIdx.x)
 // --------------------------------------------------------------------------
-constexpr int kRedSeg = 8;
+// blockDim.x = nseg * STRIDE threads, nseg <= kRedSeg: thread (c, seg) sums items seg, seg + nseg, ..., the nseg
+// segment sums are added in order.  The partials come from other CTAs (possibly of this launch): L2 loads.
 template <int STRIDE>
 __device__ __forceinline__ void block_reduce_items(const double* part, int item0, int item1,
                                                    double* s_buf /* [kRedSeg][STRIDE] */) {
-  const int c = threadIdx.x % STRIDE, seg = threadIdx.x / STRIDE;
+  const int c = threadIdx.x % STRIDE, seg = threadIdx.x / STRIDE, nseg = blockDim.x / STRIDE;
   double s = 0.0;
-  for (int i = item0 + seg; i < item1; i += kRedSeg) s += part[(size_t)i * STRIDE + c];
-  s_buf[seg * STRIDE + c] = s;
+  if (seg < nseg) {
+    // eight independent loads in flight per thread (the chain of dependent L2 round trips used to dominate)
+    for (int i = item0 + seg; i < item1; i += 8 * nseg) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = i + k * nseg;
+        v[k] = j < item1 ? __ldcg(part + (size_t)j * STRIDE + c) : 0.0;
+      }
+      s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+  }
+  if (seg < kRedSeg) s_buf[seg * STRIDE + c] = s;
   __syncthreads();
   if (seg == 0) {
     double tot = 0.0;
-#pragma unroll
-    for (int g = 0; g < kRedSeg; ++g) tot += s_buf[g * STRIDE + c];
+    for (int g = 0; g < nseg; ++g) tot += s_buf[g * STRIDE + c];
     s_buf[c] = tot;
   }
   __syncthreads();
@@ -565,7 +590,92 @@ __device__ inline void unpack_U(const double* r, double* U, double* gu) {
   for (int i = 0; i < 9; ++i) gu[i] = r[16 + i];
 }
 
-// accept / reject for one problem, given its reduced sweep partial r (one thread)
+// index into the reduced sweep partial of U(a, b), a <= b (layout at the top of the file), or -1: structural zero
+__device__ __forceinline__ int u_partial_index(int a, int b) {
+  if (b < 4) {
+    if (a == 0 && b == 0) return 1;
+    if (a == 0 && b == 2) return 2;
+    if (a == 2 && b == 2) return 3;
+    if (a == 1 && b == 1) return 4;
+    if (a == 1 && b == 3) return 5;
+    if (a == 3 && b == 3) return 6;
+    return -1;
+  }
+  const int c = b - 4;
+  if (a == 0) return 25 + c;
+  if (a == 2) return 30 + c;
+  if (a == 1) return 35 + c;
+  if (a == 3) return 40 + c;
+  const int e = a - 4;
+  return 45 + e * 5 - e * (e - 1) / 2 + (c - e);
+}
+
+// Accept / reject after a sweep, one CTA per problem (k_intr_decide; all threads call).  REDUCE: 1 sum the partials here (single GPU), 2 also all-reduce
+// them over peer memory, 0 read the (NCCL all-reduced) red_sweep buffer.  The head of the LM state is staged in
+// shared memory: thread 0 runs the state machine there (it used to walk global memory), all threads write it
+// back and, on acceptance, unpack U and g_u.
+template <int REDUCE>
+__device__ __forceinline__ void decide_tail(const IntrDev& d, const LmParams& P, const PeerComm& pc, int problem,
+                                            double* s_buf /* shared, kRedSeg * 64 doubles */) {
+  __shared__ double s_lm[kLmHeadWords];
+  __shared__ int s_accept;
+  IntrState& ps = d.ps[problem];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool evaluated = ps.lm.solve_ok != 0;
+  if (evaluated) {
+    if (REDUCE) {
+      block_reduce_items<kSweepPart>(d.sweep_part, ps.item0, ps.item1, s_buf);
+      // partitioned problem: every rank holds the same LM state, so all of them are here
+      if (REDUCE == 2) peer_allreduce64(s_buf, pc);
+    } else {
+      if (tid < kSweepPart) s_buf[tid] = d.red_sweep[(size_t)problem * kSweepPart + tid];
+    }
+  }
+  if (tid < kLmHeadWords) s_lm[tid] = reinterpret_cast<const double*>(&ps.lm)[tid];
+  __syncthreads();
+  const double* r = s_buf;
+  if (tid == 0) {
+    LmState& s = *reinterpret_cast<LmState*>(s_lm);  // only the head is touched; the trace row goes to ps.lm.hist
+    bool accept = false;
+    if (!evaluated) {
+      // the linear solve failed (non-PD): shrink the trust region and retry
+      lm_reject(s, P, d.n_done);
+      s.solve_ok = 1;
+      if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, d.n_done, true);
+    } else if (r[kSweepPart - 1] < 0.0) {  // the peer-memory allreduce timed out
+      lm_finish(s, CCG_ERR_NCCL, d.n_done, false);
+    } else {
+      accept = lm_decide(s, P, 0.5 * r[0], r[7] + s.gTd_u, r[8] + s.dDd_u, d.n_done, ps.lm.hist);
+      if (accept) {
+        s.n_obs = r[3];
+        s.sumsq = r[0];
+      }
+    }
+    s_accept = accept ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid < kLmHeadWords) reinterpret_cast<double*>(&ps.lm)[tid] = s_lm[tid];
+  if (s_accept) {
+    for (int e = tid; e < 90; e += nt) {
+      if (e < 81) {
+        const int a = e / 9, b = e - 9 * a;
+        const int idx = u_partial_index(a < b ? a : b, a < b ? b : a);
+        ps.U[e] = idx >= 0 ? r[idx] : 0.0;
+      } else {
+        ps.gu[e - 81] = r[16 + e - 81];
+      }
+    }
+  }
+}
+
+template <int REDUCE>
+__global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_decide(IntrDev d, LmParams P, PeerComm pc) {
+  __shared__ double s_buf[kRedSeg * kSweepPart];
+  if (d.ps[blockIdx.x].lm.status != 0) return;
+  decide_tail<REDUCE>(d, P, pc, blockIdx.x, s_buf);
+}
+
+// accept / reject for one problem, given its reduced sweep partial r (one thread; batches of small problems)
 __device__ inline void decide_body(IntrState& ps, const LmParams& P, bool evaluated, const double* r, int* n_done) {
   LmState& s = ps.lm;
   if (!evaluated) {
@@ -573,10 +683,6 @@ __device__ inline void decide_body(IntrState& ps, const LmParams& P, bool evalua
     lm_reject(s, P, n_done);
     s.solve_ok = 1;
     if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, n_done, true);
-    return;
-  }
-  if (r[kSweepPart - 1] < 0.0) {  // the peer-memory allreduce timed out
-    lm_finish(s, CCG_ERR_NCCL, n_done, false);
     return;
   }
   const double cost_c = 0.5 * r[0];
@@ -588,38 +694,11 @@ __device__ inline void decide_body(IntrState& ps, const LmParams& P, bool evalua
   }
 }
 
-// accept / reject after a sweep.  REDUCE: sum the partials here (single GPU);
-// otherwise read the (all-reduced) red_sweep buffer.
-template <int REDUCE>
-__global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_decide(IntrDev d, LmParams P, PeerComm pc) {
-  __shared__ double s_buf[kRedSeg * kSweepPart];
-  IntrState& ps = d.ps[blockIdx.x];
-  if (ps.lm.status != 0) return;
-  const bool evaluated = ps.lm.solve_ok != 0;
-  if (evaluated) {
-    if (REDUCE) {
-      block_reduce_items<kSweepPart>(d.sweep_part, ps.item0, ps.item1, s_buf);
-      // partitioned problem: every rank holds the same LM state, so all of them are here
-      if (REDUCE == 2) peer_allreduce64(s_buf, pc);
-    } else {
-      if (threadIdx.x < kSweepPart) s_buf[threadIdx.x] = d.red_sweep[(size_t)blockIdx.x * kSweepPart + threadIdx.x];
-      __syncthreads();
-    }
-  }
-  if (threadIdx.x != 0) return;
-  decide_body(ps, P, evaluated, s_buf, d.n_done);
-}
-
-// reduced 9x9 solve for one problem, given its reduced elimination partial r (one thread)
+// reduced 9x9 solve for one problem, given its reduced elimination partial r (one thread; batches of small problems)
 __device__ inline void solve_body(IntrState& ps, const LmParams& P, const double* r, int* n_done) {
   LmState& s = ps.lm;
   const unsigned mask = ps.mask;
   const int par = s.par;
-  if (r[kSchurPart - 1] < 0.0) {  // the peer-memory allreduce timed out
-    s.finalize = 0;
-    if (s.status == 0) lm_finish(s, CCG_ERR_NCCL, n_done, false);
-    return;
-  }
   double gDg = r[54];
   for (int k = 0; k < 9; ++k)
     if (!((mask >> k) & 1u) && ps.U[k * 9 + k] > 0.0) gDg += ps.gu[k] * ps.gu[k] / ps.U[k * 9 + k];
@@ -673,21 +752,113 @@ __device__ inline void solve_body(IntrState& ps, const LmParams& P, const double
   s.solve_ok = 1;
 }
 
-// reduced 9x9 solve.  Also evaluates the gradient norm at the current point.
+// Reduced 9x9 solve, one CTA per problem (k_intr_solve; REDUCE as in decide_tail).  Also evaluates the gradient norm at the current point.  State
+// head, U, g_u in shared memory; the system is assembled in parallel and solved by one thread in registers
+// (chol_solve_reg) instead of one thread walking global and local memory.
 template <int REDUCE>
-__global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, LmParams P, PeerComm pc) {
-  __shared__ double s_buf[kRedSeg * kSchurPart];
-  IntrState& ps = d.ps[blockIdx.x];
-  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
+__device__ __forceinline__ void solve_tail(const IntrDev& d, const LmParams& P, const PeerComm& pc, int problem,
+                                           double* s_buf /* shared, kRedSeg * 64 doubles */) {
+  __shared__ double s_lm[kLmHeadWords];
+  __shared__ double s_U[81], s_S[81], s_gu[9], s_rhs[9], s_Du[9], s_x[9];
+  __shared__ int s_go;
+  IntrState& ps = d.ps[problem];
+  const int tid = threadIdx.x, nt = blockDim.x;
   if (REDUCE) {
     block_reduce_items<kSchurPart>(d.schur_part, ps.item0 * d.schur_split, ps.item1 * d.schur_split, s_buf);
     if (REDUCE == 2) peer_allreduce64(s_buf, pc);
   } else {
-    if (threadIdx.x < kSchurPart) s_buf[threadIdx.x] = d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x];
+    if (tid < kSchurPart) s_buf[tid] = d.red_schur[(size_t)problem * kSchurPart + tid];
+  }
+  if (tid < kLmHeadWords) s_lm[tid] = reinterpret_cast<const double*>(&ps.lm)[tid];
+  for (int e = tid; e < 90; e += nt) {
+    if (e < 81) s_U[e] = ps.U[e];
+    else s_gu[e - 81] = ps.gu[e - 81];
+  }
+  __syncthreads();
+  const double* r = s_buf;
+  const unsigned mask = ps.mask;
+  LmState& s = *reinterpret_cast<LmState*>(s_lm);  // only the head is touched
+  if (tid == 0) {
+    int go = 0;
+    if (r[kSchurPart - 1] < 0.0) {  // the peer-memory allreduce timed out
+      s.finalize = 0;
+      if (s.status == 0) lm_finish(s, CCG_ERR_NCCL, d.n_done, false);
+    } else {
+      double gDg = r[54];
+      for (int k = 0; k < 9; ++k)
+        if (!((mask >> k) & 1u) && s_U[k * 9 + k] > 0.0) gDg += s_gu[k] * s_gu[k] / s_U[k * 9 + k];
+      const double rnorm = sqrt(2.0 * s.cost);
+      s.grad_norm = rnorm > 0.0 ? sqrt(gDg) / rnorm : 0.0;
+      if (s.finalize) {
+        s.finalize = 0;
+      } else if (s.cost == 0.0 || sqrt(gDg) <= P.gradient_tolerance * rnorm) {
+        lm_finish(s, 1, d.n_done, false);
+      } else {
+        s.iterations++;
+        if (r[55] > 0.0) s.solve_ok = 0;
+        else go = 1;
+      }
+    }
+    s_go = go;
+  }
+  __syncthreads();
+  if (s_go) {
+    const double lambda = s.lambda;
+    for (int e = tid; e < 90; e += nt) {
+      if (e < 81) {
+        const int a = e / 9, b = e - 9 * a;
+        double v = s_U[e] - (a <= b ? r[up9(a, b)] : r[up9(b, a)]);  // packed upper triangle of W'V'^-1W
+        if (a == b) v += lambda * clampd(s_U[e], P.min_diagonal, P.max_diagonal);
+        if (((mask >> a) & 1u) || ((mask >> b) & 1u)) v = a == b ? 1.0 : 0.0;
+        s_S[e] = v;
+      } else {
+        const int a = e - 81;
+        s_Du[a] = clampd(s_U[a * 9 + a], P.min_diagonal, P.max_diagonal);
+        s_rhs[a] = ((mask >> a) & 1u) ? 0.0 : -s_gu[a] + r[45 + a];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // 9 x 9: one thread, everything in registers (a warp-cooperative solve through shared memory was slower:
+      // it serialises 27 double-precision divisions and square roots behind warp barriers)
+      double x[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) x[k] = s_rhs[k];
+      const bool ok = chol_solve_reg<9>(s_S, x);
+      if (ok) {
+        double gTd = 0.0, dDd = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const double dk = ((mask >> k) & 1u) ? 0.0 : x[k];
+          s_x[k] = dk;
+          gTd += s_gu[k] * dk;
+          dDd += dk * dk * s_Du[k];
+        }
+        s.gTd_u = gTd;
+        s.dDd_u = dDd;
+        s.solve_ok = 1;
+      } else {
+        s.solve_ok = 0;
+      }
+      s_go = ok ? 2 : 0;
+    }
+    __syncthreads();
+    if (s_go == 2 && tid < 9) {
+      const int par = s.par;
+      ps.du[tid] = s_x[tid];
+      ps.intr[par ^ 1][tid] = ps.intr[par][tid] + s_x[tid];
+    }
     __syncthreads();
   }
-  if (threadIdx.x != 0) return;
-  solve_body(ps, P, s_buf, d.n_done);
+  if (tid < kLmHeadWords) reinterpret_cast<double*>(&ps.lm)[tid] = s_lm[tid];
+}
+
+template <int REDUCE>
+__global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, LmParams P, PeerComm pc) {
+  const IntrState& ps = d.ps[blockIdx.x];
+  __shared__ double s_buf[kRedSeg * kSchurPart];
+  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
+  solve_tail<REDUCE>(d, P, pc, blockIdx.x, s_buf);
 }
 
 // Batches of small problems (every problem is a single work item): one THREAD per problem
@@ -908,15 +1079,18 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   CCG_TRY(dev_alloc(p, &d.blk[1], (size_t)n_views * kBlk));
   CCG_TRY(dev_alloc(p, &d.yz, (size_t)n_views * kYz));
   CCG_TRY(dev_alloc(p, &d.sweep_part, items.size() * kSweepPart));
-  // elimination and candidate-pose kernels: 64 views per CTA pass, one pass per CTA (a partition of a
+  // elimination kernel: 64 views per CTA pass, one pass per CTA (a partition of a
   // large problem over 8 GPUs leaves ~85 views per item: two half-empty passes would double its latency)
   int64_t max_item_views = 1;
   for (const WorkItem& w : items) max_item_views = std::max<int64_t>(max_item_views, w.v1 - w.v0);
-  const int schur_split = (int)std::max<int64_t>(1, std::min<int64_t>((max_item_views + 63) / 64, 32));
+  // CTAs of the elimination kernel per work item: one 64-view pass each while that keeps the grid within ~4 CTAs
+  // per SM (every CTA adds a partial to the reduction that follows), several passes per CTA beyond
+  const int per_pass = kSchurWarps * 32;
+  const int64_t cap = std::max<int64_t>(1, (4 * (int64_t)ctx->sm_count) / std::max<int64_t>(1, (int64_t)items.size()));
+  const int schur_split = (int)std::max<int64_t>(1, std::min<int64_t>((max_item_views + per_pass - 1) / per_pass, cap));
   CCG_TRY(dev_alloc(p, &d.schur_part, items.size() * (size_t)schur_split * kSchurPart));
   CCG_TRY(dev_alloc(p, &d.rt, (size_t)n_views * 12));
   CCG_TRY(dev_alloc(p, &d.rtf, (size_t)n_views * 12));
-  CCG_TRY(dev_alloc(p, &d.step_part, items.size() * (size_t)schur_split * 2));
   CCG_TRY(dev_alloc(p, &d.red_sweep, (size_t)n_problems * kSweepPart));
   CCG_TRY(dev_alloc(p, &d.red_schur, (size_t)n_problems * kSchurPart));
   CCG_TRY(dev_alloc(p, &d.ps, (size_t)n_problems));
@@ -1020,38 +1194,30 @@ void launch_sweep_ws_t(ccg_intr_problem* p, double* res_out) {
   k_intr_sweep_ws<RES><<<p->n_items, kSwThreads, kSwSmem, ctx->stream>>>(p->dev, res_out);
 }
 
-// the sweep kernel variant: warp-specialised tensor-core sweep (after the candidate-pose kernel), or
-// everything in FP64 with a warp pair per view
-void launch_sweep(ccg_intr_problem* p, const LmParams& P, double* res_out) {
-  cudaStream_t st = p->ctx->stream;
-  if (P.hessian_fp64 == 0) {
-    k_intr_step<<<p->n_items * p->dev.schur_split, kStepThreads, 0, st>>>(p->dev);
-    p->ctx->launches++;
-    if (res_out) launch_sweep_ws_t<true>(p, res_out);
-    else launch_sweep_ws_t<false>(p, res_out);
-  } else {
-    k_intr_sweep<<<p->n_items, kWarps * 32, 0, st>>>(p->dev, res_out);
-  }
-  p->ctx->launches++;
-}
-
 // one residual+Jacobian sweep followed by the accept/reject step
 int launch_sweep_decide(ccg_intr_problem* p, const LmParams& P, Profiler& prof, double* res_out, int* n_allreduce) {
   ccg_ctx* ctx = p->ctx;
   IntrDev& d = p->dev;
   cudaStream_t st = ctx->stream;
   const int nb = (int)p->n_problems;
+  const PeerComm pc = peer_comm(ctx);
+  const bool partitioned = p->shared && ctx->world > 1;
   prof.begin(TAG_SWEEP);
-  launch_sweep(p, P, res_out);
+  if (P.hessian_fp64 == 0) {
+    // default: candidate poses + warp-specialised tensor-core sweep in one launch
+    if (res_out) launch_sweep_ws_t<true>(p, res_out);
+    else launch_sweep_ws_t<false>(p, res_out);
+  } else {
+    k_intr_sweep<<<p->n_items, kWarps * 32, 0, st>>>(d, res_out);  // everything in FP64, a warp pair per view
+  }
+  ctx->launches++;
   prof.end();
   prof.begin(TAG_SMALL);
-  const PeerComm pc = peer_comm(ctx);
-  if (p->shared && ctx->world > 1 && ctx->peer_ok) {
-    // reduce + allreduce over peer memory + accept/reject in ONE kernel
+  if (partitioned && ctx->peer_ok) {
     k_intr_decide<2><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P, pc);
     (*n_allreduce)++;
     ctx->launches++;
-  } else if (p->shared && ctx->world > 1) {
+  } else if (partitioned) {
     k_intr_reduce_sweep<<<nb, kRedSeg * kSweepPart, 0, st>>>(d);
     CCG_TRY(nccl_allreduce_sum(ctx, d.red_sweep, (size_t)nb * kSweepPart));
     (*n_allreduce)++;
@@ -1073,17 +1239,18 @@ int launch_schur_solve(ccg_intr_problem* p, const LmParams& P, Profiler& prof, i
   IntrDev& d = p->dev;
   cudaStream_t st = ctx->stream;
   const int nb = (int)p->n_problems;
+  const PeerComm pc = peer_comm(ctx);
+  const bool partitioned = p->shared && ctx->world > 1;
   prof.begin(TAG_SCHUR);
   k_intr_schur<<<p->n_items * d.schur_split, kSchurWarps * 32, 0, st>>>(d, P);
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
-  const PeerComm pc = peer_comm(ctx);
-  if (p->shared && ctx->world > 1 && ctx->peer_ok) {
+  if (partitioned && ctx->peer_ok) {
     k_intr_solve<2><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P, pc);
     (*n_allreduce)++;
     ctx->launches++;
-  } else if (p->shared && ctx->world > 1) {
+  } else if (partitioned) {
     k_intr_reduce_schur<<<nb, kRedSeg * kSchurPart, 0, st>>>(d);
     CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, (size_t)nb * kSchurPart));
     (*n_allreduce)++;
@@ -1311,9 +1478,15 @@ int ccg_intrinsics_time_sweep(ccg_intr_problem* p, int n, float* ms_per_launch) 
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  launch_sweep(p, P, nullptr);  // warm-up
+  // the sweep alone (no accept/reject in between): every launch evaluates the same (initial) point
+  auto sweep = [&]() {
+    if (P.hessian_fp64 == 0) launch_sweep_ws_t<false>(p, nullptr);
+    else k_intr_sweep<<<p->n_items, kWarps * 32, 0, ctx->stream>>>(p->dev, nullptr);
+    ctx->launches++;
+  };
+  sweep();  // warm-up
   cudaEventRecord(e0, ctx->stream);
-  for (int i = 0; i < n; ++i) launch_sweep(p, P, nullptr);
+  for (int i = 0; i < n; ++i) sweep();
   cudaEventRecord(e1, ctx->stream);
   CCG_CUDA(ctx, cudaEventSynchronize(e1));
   float ms = 0.f;

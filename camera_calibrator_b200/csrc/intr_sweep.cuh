@@ -513,35 +513,15 @@ __device__ __forceinline__ T* opaque_ptr(T* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Candidate poses, one thread per view: pose (+) delta_v with delta_v = -z - Y du (the
-// back-substitution of the reduced solve), written as the candidate pose and as the rotation
-// matrix + translation the sweep consumes; per-CTA partial sums of the model terms g'd and d'Dd.
-// Grid: schur_split CTAs per work item (the elimination kernel's split).
+// Candidate poses of the item's views, by all threads of the sweep CTA before the roles start (one thread
+// per view): pose (+) delta_v with delta_v = -z - Y du (the back-substitution of the reduced solve), written
+// as the candidate pose and as the rotation matrix + translation the roles consume (double and float);
+// s_step[0..1] receive the item's share of the model terms g'd and d'Dd (fixed-order sums).
 // ---------------------------------------------------------------------------------------------
-constexpr int kStepThreads = 128;
-__global__ void __launch_bounds__(kStepThreads) k_intr_step(IntrDev d) {
-  __shared__ double s_du[9];
-  __shared__ double s_red[2][kStepThreads / 32];
-  __shared__ int s_meta[2];
-  WorkItem it = d.items[blockIdx.x / d.schur_split];
-  {
-    const int sub = blockIdx.x % d.schur_split, nv = it.v1 - it.v0;
-    const int a = it.v0 + (int)((int64_t)nv * sub / d.schur_split);
-    const int b = it.v0 + (int)((int64_t)nv * (sub + 1) / d.schur_split);
-    it.v0 = a;
-    it.v1 = b;
-  }
-  IntrState& ps = d.ps[it.problem];
-  if (threadIdx.x == 0) {
-    s_meta[0] = ps.lm.par;
-    s_meta[1] = (ps.lm.status == 0 && ps.lm.solve_ok) ? 1 : 0;
-  }
-  if (threadIdx.x < 9) s_du[threadIdx.x] = ps.du[threadIdx.x];
-  __syncthreads();
-  if (!s_meta[1]) return;
-  const int par = s_meta[0];
+__device__ __forceinline__ void sw_candidate_poses(const IntrDev& d, const WorkItem& it, int par, const double* s_du,
+                                                   double (*s_red)[kSwWarps], double* s_step) {
   double gTd = 0.0, dDd = 0.0;
-  for (int64_t v = it.v0 + threadIdx.x; v < it.v1; v += kStepThreads) {
+  for (int64_t v = it.v0 + threadIdx.x; v < it.v1; v += kSwThreads) {
     const double* yz = d.yz + (size_t)v * kYz;
     double dl[6];
 #pragma unroll
@@ -584,14 +564,15 @@ __global__ void __launch_bounds__(kStepThreads) k_intr_step(IntrDev d) {
     s_red[0][threadIdx.x >> 5] = gTd;
     s_red[1][threadIdx.x >> 5] = dDd;
   }
-  __syncthreads();
+  __syncthreads();  // also: the poses are visible to the whole CTA
   if (threadIdx.x < 2) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kStepThreads / 32; ++w) s += s_red[threadIdx.x][w];
-    d.step_part[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+    for (int w = 0; w < kSwWarps; ++w) s += s_red[threadIdx.x][w];
+    s_step[threadIdx.x] = s;
   }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // The FP64 role over the views [va, vb) (absolute view indices): residuals, cost, g_u (into the
@@ -633,13 +614,13 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, c
     double2 pn[6];
     if (!LEAN) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) pn[i] = __ldg(rt + (size_t)va * 6 + i);
+      for (int i = 0; i < 6; ++i) pn[i] = rt[(size_t)va * 6 + i];
     }
     int n_next = vmeta[va].y;
     for (int v = va; v < vb; ++v) {
       if (LEAN) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) pn[i] = __ldg(rt + (size_t)v * 6 + i);
+        for (int i = 0; i < 6; ++i) pn[i] = rt[(size_t)v * 6 + i];
       }
       const double R[9] = {pn[0].x, pn[0].y, pn[1].x, pn[1].y, pn[2].x, pn[2].y, pn[3].x, pn[3].y, pn[4].x};
       const double t[3] = {pn[4].y, pn[5].x, pn[5].y};
@@ -649,7 +630,7 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, c
         const int vn = min(v + 1, vb - 1);
         if (!LEAN) {
 #pragma unroll
-          for (int i = 0; i < 6; ++i) pn[i] = __ldg(rt + (size_t)vn * 6 + i);
+          for (int i = 0; i < 6; ++i) pn[i] = rt[(size_t)vn * 6 + i];
         }
         n_next = vmeta[vn].y;
       }
@@ -743,7 +724,7 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
   const unsigned frag = tile + (unsigned)(2 * tig * kTcRow + 2 * g) * 4;  // this lane's fragment of k-step 0
   float4 pn[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) pn[i] = __ldg(rtf + (size_t)va * 3 + i);
+  for (int i = 0; i < 3; ++i) pn[i] = rtf[(size_t)va * 3 + i];
   int n_next = vmeta[va].y;
   for (int v = va; v < vb; ++v) {
     const float Rf[9] = {pn[0].x, pn[0].y, pn[0].z, pn[0].w, pn[1].x, pn[1].y, pn[1].z, pn[1].w, pn[2].x};
@@ -752,7 +733,7 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
     {
       const int vn = min(v + 1, vb - 1);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) pn[i] = __ldg(rtf + (size_t)vn * 3 + i);
+      for (int i = 0; i < 3; ++i) pn[i] = rtf[(size_t)vn * 3 + i];
       n_next = vmeta[vn].y;
     }
     // product columns 0..7 (c0*) and 8..15 (c1*), two accumulator sets each
@@ -821,7 +802,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, doub
   float* s_stage_d = reinterpret_cast<float*>(s_dyn + sizeof(double) * kSwWarps * kSweepPart);
   float* s_stage_j = s_stage_d + kSwPairs * kSwStagesD * kSwStageD;
   float* s_tiles = s_stage_j + kSwPairs * kSwStagesJ * kSwStageJ;
-  __shared__ double s_k[9];
+  __shared__ double s_k[9], s_du[9], s_step[2];
+  __shared__ double s_red[2][kSwWarps];
   __shared__ int s_meta[2];
   const WorkItem it = d.items[blockIdx.x];
   IntrState& ps = d.ps[it.problem];
@@ -831,55 +813,55 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, doub
   }
   __syncthreads();
   if (!s_meta[1]) return;
-  const int par = s_meta[0];
-  if (threadIdx.x < 9) s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
-  for (int i = threadIdx.x; i < kSwWarps * kSweepPart; i += kSwThreads) (&s_part[0][0])[i] = 0.0;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* upart = s_part[warp];
-  // pair p (Jacobian warp p, FP64 warp kSwPairs + p, same SM sub-partition) owns the p-th part of the item's views
-  const int pair = warp & (kSwPairs - 1), nv = it.v1 - it.v0;
-  const int va = it.v0 + (int)((int64_t)nv * pair / kSwPairs), vb = it.v0 + (int)((int64_t)nv * (pair + 1) / kSwPairs);
-  const int vsplit = va + ((vb - va) * (64 - kSwTail) + 32) / 64;  // FP64 role: [va, vsplit) the FP64 warp, the rest its partner
-#ifdef CCG_SW_D_FIRST  // experiment: which warp ids the issue arbiter prefers
-  if (warp < kSwPairs) {
-#else
-  if (warp >= kSwPairs) {
-#endif
-    // =========================== FP64 role ===========================
-    if (kSwRegD > kSwRegLaunch) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSwRegD));
+  {
+    const int par = s_meta[0];
+    if (threadIdx.x < 9) {
+      s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
+      s_du[threadIdx.x] = ps.du[threadIdx.x];
+    }
+    for (int i = threadIdx.x; i < kSwWarps * kSweepPart; i += kSwThreads) (&s_part[0][0])[i] = 0.0;
+    __syncthreads();
+    sw_candidate_poses(d, it, par, s_du, s_red, s_step);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* upart = s_part[warp];
+    // pair p (Jacobian warp p, FP64 warp kSwPairs + p, same SM sub-partition) owns the p-th part of the item's views
+    const int pair = warp & (kSwPairs - 1), nv = it.v1 - it.v0;
+    const int va = it.v0 + (int)((int64_t)nv * pair / kSwPairs), vb = it.v0 + (int)((int64_t)nv * (pair + 1) / kSwPairs);
+    const int vsplit = va + ((vb - va) * (64 - kSwTail) + 32) / 64;  // FP64 role: [va, vsplit) the FP64 warp, the rest its partner
+    if (warp >= kSwPairs) {
+      // =========================== FP64 role ===========================
+      if (kSwRegD > kSwRegLaunch) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSwRegD));
 #ifndef CCG_SW_ONLY_J  // timing experiments: one role alone (results are then incomplete)
-    sw_run_fp64<RES, false>(d, smem_u32(s_stage_d + pair * kSwStagesD * kSwStageD), s_k, par, va, vsplit, lane, upart,
-                            res_out);
+      sw_run_fp64<RES, false>(d, smem_u32(s_stage_d + pair * kSwStagesD * kSwStageD), s_k, par, va, vsplit, lane, upart,
+                              res_out);
 #endif
-  } else {
-    // =========================== Jacobian + tensor role ===========================
-    if (kSwRegJ < kSwRegLaunch) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSwRegJ));
+    } else {
+      // =========================== Jacobian + tensor role ===========================
+      if (kSwRegJ < kSwRegLaunch) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSwRegJ));
 #ifndef CCG_SW_ONLY_D
-    sw_run_jac(d, smem_u32(s_stage_j + pair * kSwStagesJ * kSwStageJ), smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k, par, va, vb,
-               lane, upart);
+      sw_run_jac(d, smem_u32(s_stage_j + pair * kSwStagesJ * kSwStageJ), smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k,
+                 par, va, vb, lane, upart);
 #endif
 #if !defined(CCG_SW_ONLY_J) || defined(CCG_SW_TAIL_ANYWAY)
-    // the tail of the pair's FP64 work; the ring lives in the tile(s), free by now (every lane is past its last
-    // tile read: sw_run_fp64 synchronises the warp before the first ring write lands)
-    if (kSwTail > 0) {
-      __syncwarp();
-      sw_run_fp64<RES, true>(d, smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k, par, vsplit, vb, lane, upart, res_out);
-    }
+      // the tail of the pair's FP64 work; the ring lives in the tile(s), free by now (every lane is past its last
+      // tile read: sw_run_fp64 synchronises the warp before the first ring write lands)
+      if (kSwTail > 0) {
+        __syncwarp();
+        sw_run_fp64<RES, true>(d, smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k, par, vsplit, vb, lane, upart, res_out);
+      }
 #endif
-  }
-  __syncthreads();
-  if (threadIdx.x < kSweepPart) {
-    // the model terms g'd, d'Dd of this item come from the candidate-pose kernel
-    double s = 0.0;
-    if (threadIdx.x == 7 || threadIdx.x == 8) {
-      const int c = threadIdx.x - 7;
-      for (int i = 0; i < d.schur_split; ++i) s += d.step_part[((size_t)blockIdx.x * d.schur_split + i) * 2 + c];
-    } else {
-#pragma unroll
-      for (int w = 0; w < kSwWarps; ++w) s += s_part[w][threadIdx.x];
     }
-    d.sweep_part[(size_t)blockIdx.x * kSweepPart + threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < kSweepPart) {
+      double s = 0.0;
+      if (threadIdx.x == 7 || threadIdx.x == 8) {
+        s = s_step[threadIdx.x - 7];  // the model terms g'd, d'Dd of this item
+      } else {
+#pragma unroll
+        for (int w = 0; w < kSwWarps; ++w) s += s_part[w][threadIdx.x];
+      }
+      d.sweep_part[(size_t)blockIdx.x * kSweepPart + threadIdx.x] = s;
+    }
   }
 }
 

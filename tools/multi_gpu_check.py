@@ -45,6 +45,32 @@ all_i = [torch.zeros(9, dtype=torch.float64, device="cuda") for _ in range(world
 dist.all_gather(all_i, torch.tensor(gi[0], device="cuda"))
 ok &= all(torch.equal(all_i[0], x) for x in all_i)  # replicated state is bit-identical on every rank
 
+# ---- the ranks' largest |measurement| differ by more than 10 %: the cost-resolution threshold of the LM state machine
+# must come from the GLOBAL maximum or the replicated state machines can take different branches (hang / timeout)
+keep = np.ones(full.u.size, dtype=bool)
+view_of = np.repeat(np.arange(V), np.diff(full.view_offsets))
+keep[(view_of >= V // world) & ((full.u > 1300.0) | (full.v > 850.0))] = False  # crop every rank's views but rank 0's
+cu, cv, cX, cY, cZ = (x[keep] for x in (full.u, full.v, full.X, full.Y, full.Z))
+coff = np.concatenate([[0], np.cumsum(np.bincount(view_of[keep], minlength=V))]).astype(np.int64)
+(u2, v2, X2, Y2, Z2), off2 = partition.slice_views([cu, cv, cX, cY, cZ], coff, a, b)
+local_max = float(max(np.abs(u2).max(), np.abs(v2).max()))
+p2 = ctx.intrinsics_problem(u2, v2, X2, Y2, Z2, off2, intr, q[a:b], t[a:b], shared=True)
+p2.run()
+hi, hq, ht, hrep = p2.download()
+maxes = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+dist.all_gather(maxes, torch.tensor([local_max], dtype=torch.float64, device="cuda"))
+if rank == 0:
+    ri2, _, rt2, rrep2 = ctx1.intrinsics_solve(cu, cv, cX, cY, cZ, coff, intr, q, t)
+    e_i2 = float(np.max(np.abs(hi[0] - ri2) / np.abs(ri2)))
+    e_r2 = abs(hrep[0]["rms"] - rrep2["rms"])
+    print(f"[intr, unequal measurement ranges] per-rank max |measurement| {[round(float(m.item()), 1) for m in maxes]}: "
+          f"intr rel err {e_i2:.2e}  |d rms| {e_r2:.2e}  termination {hrep[0]['termination']} vs {rrep2['termination']}  "
+          f"sweeps {hrep[0]['sweeps']} vs {rrep2['sweeps']}")
+    ok &= e_i2 <= 1e-6 and e_r2 <= 1e-9 and hrep[0]["termination"] in (1, 2, 3)
+all_h = [torch.zeros(9, dtype=torch.float64, device="cuda") for _ in range(world)]
+dist.all_gather(all_h, torch.tensor(hi[0], device="cuda"))
+ok &= all(torch.equal(all_h[0], x) for x in all_h)
+
 # ---- rig, frames partitioned
 s = synth.rig_scene(n_cams=4, n_frames=400, grid=(7, 5), seed=6)
 fa, fb = partition.split_range(400, world, rank)
