@@ -84,8 +84,16 @@ constexpr int kObsBlock = 160;   // floats per 32-observation block in HBM: u v 
 constexpr int kSwStageD = 160;   // floats per stage: the whole block
 constexpr int kSwStageJ = 96;    // floats per stage: X Y Z
 
-constexpr int kTcRow = 20;            // floats per Jacobian row in the tile (16 + 4: conflict-free STS.128 and LDS.64)
-constexpr int kTcTile = 64 * kTcRow;  // one 32-observation tile
+// Operand format of the J'J products: 1 = FP16 pairs (u row, v row) per column, mma m16n8k16 (the legacy tensor
+// path issues one m16n8k8 or m16n8k16 per 8.6 cycles and SM sub-partition and shares its pipe with FP64, so half
+// the instructions is half the pipe time; FP16 carries the same 11 significant bits as TF32; the pose columns are
+// scaled by a power of two so that no entry leaves the FP16 range), 0 = TF32 rows, mma m16n8k8.
+#ifndef CCG_SW_F16
+#define CCG_SW_F16 1
+#endif
+constexpr bool kSwF16 = CCG_SW_F16 != 0;
+constexpr int kTcRow = 20;            // 32-bit words per tile row (16 + 4: conflict-free STS.128 and LDS.64)
+constexpr int kTcTile = (kSwF16 ? 32 : 64) * kTcRow;  // one 32-observation tile: a row per observation (FP16 pairs) or per residual
 
 constexpr size_t kSwSmem = sizeof(double) * kSwWarps * kSweepPart +
                            sizeof(float) * kSwPairs * (kSwStagesD * kSwStageD + kSwStagesJ * kSwStageJ + kSwTiles * kTcTile);
@@ -98,6 +106,20 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], unsigned a0, unsi
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void mma_f16_16x8x16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2,
+                                                unsigned a3, unsigned b0, unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// (lo, hi) -> two FP16 in one register, round to nearest, saturating (an out-of-range entry must not become Inf)
+__device__ __forceinline__ unsigned pack_f16x2(float lo, float hi) {
+  unsigned d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 // destination of element (row, col) of the per-view 16 x 16 product inside the view block
@@ -139,6 +161,7 @@ struct TcConst64 {
 };
 struct TcConst32 {
   float fx, fy, k1, k2, p1, p2, k3;
+  float sp;  // power-of-two scale of the six pose columns (FP16 operands), 1 otherwise
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -330,8 +353,8 @@ __device__ __forceinline__ void tc_fp32_rows(const TcConst32& K, const float (&R
   const float F00 = fmaf(2.0f, u2, fmaf(a2 - r2, mp, base));
   const float F01 = fmaf(a1, mp, fmaf(K.p1, tx, K.p2 * ty));
   const float F11 = fmaf(2.0f, u1, fmaf(a3 - r2, mp, base));
-  const float fiz = fxv * iz, giz = fyv * iz;
-  // d(u,v)/d(camera point): rows (A0 A1 A2), (B0 B1 B2)
+  const float fiz = fxv * iz * K.sp, giz = fyv * iz * K.sp;
+  // d(u,v)/d(camera point): rows (A0 A1 A2), (B0 B1 B2) (times the pose-column scale)
   const float A0 = fiz * F00, A1 = fiz * F01, B0 = giz * F01, B1 = giz * F11;
   const float A2 = -fmaf(A0, xn, A1 * yn), B2 = -fmaf(B0, xn, B1 * yn);
   // d(camera point)/d(rotation tangent) = 2 (y x .)
@@ -409,10 +432,24 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
 }
 
 __device__ __forceinline__ void tc_store_rows(unsigned row_u, const float4 (&ur)[4], const float4 (&vr)[4]) {
+  if (kSwF16) {
+    // one row per observation: word p = (u row, v row) at tile position p, as FP16
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    sts_v4f32(row_u + 16 * i, ur[i]);
-    sts_v4f32(row_u + 32 * kTcRow * 4 + 16 * i, vr[i]);
+    for (int i = 0; i < 4; ++i) {
+      uint4 w;
+      w.x = pack_f16x2(ur[i].x, vr[i].x);
+      w.y = pack_f16x2(ur[i].y, vr[i].y);
+      w.z = pack_f16x2(ur[i].z, vr[i].z);
+      w.w = pack_f16x2(ur[i].w, vr[i].w);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_u + 16 * i), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w)
+                   : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sts_v4f32(row_u + 16 * i, ur[i]);
+      sts_v4f32(row_u + 32 * kTcRow * 4 + 16 * i, vr[i]);
+    }
   }
 }
 
@@ -422,6 +459,27 @@ __device__ __forceinline__ void tc_contract(unsigned frag, int nvalid, float (&c
 #ifdef CCG_SW_NO_MMA  // timing experiment: no contraction (results are then wrong)
   return;
 #endif
+  if (kSwF16) {
+    // k-step s contracts observations 8s..8s+7: k = 2 tig, 2 tig + 1 -> (u, v) of observation 8s + 2 tig,
+    // k = 2 tig + 8, + 9 -> the next observation; a fragment register is one tile word
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (FULL || 8 * s < nvalid) {
+        const float2 lo = lds_v2f32(frag + (8 * s) * kTcRow * 4);
+        const float2 hi = lds_v2f32(frag + (8 * s + 1) * kTcRow * 4);
+        const unsigned a0 = __float_as_uint(lo.x), a1 = __float_as_uint(lo.y);
+        const unsigned a2 = __float_as_uint(hi.x), a3 = __float_as_uint(hi.y);
+        if (s & 1) {
+          mma_f16_16x8x16(c0b, a0, a1, a2, a3, a0, a2);
+          mma_f16_16x8x16(c1b, a0, a1, a2, a3, a1, a3);
+        } else {
+          mma_f16_16x8x16(c0a, a0, a1, a2, a3, a0, a2);
+          mma_f16_16x8x16(c1a, a0, a1, a2, a3, a1, a3);
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     if (FULL || 8 * (s & 3) < nvalid) {
@@ -708,6 +766,11 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
   TcConst32 K;
   K.fx = (float)s_k[0]; K.fy = (float)s_k[1];
   K.k1 = (float)s_k[4]; K.k2 = (float)s_k[5]; K.p1 = (float)s_k[6]; K.p2 = (float)s_k[7]; K.k3 = (float)s_k[8];
+  // FP16 operands: scale the pose columns so that the focal length they carry is below 512 (their entries are a
+  // few times fx / depth); undone exactly (powers of two) when the blocks are written
+  const int sp_e = kSwF16 ? max(0, ilogbf(fmaxf(fabsf(K.fx), fabsf(K.fy))) - 8) : 0;
+  K.sp = ldexpf(1.0f, -sp_e);
+  const double isp = (double)ldexpf(1.0f, sp_e);
   const int2* vmeta = opaque_ptr(d.vmeta);
   const float4* rtf = reinterpret_cast<const float4*>(opaque_ptr(d.rtf));
   double* blk0 = opaque_ptr(d.blk[par ^ 1]);
@@ -785,7 +848,7 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
       const int row = g + ((e & 2) ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
       const float val = nt == 0 ? c0a[e] + c0b[e] : c1a[e] + c1b[e];
       const int bs = tc_blk_slot(row, col), us = tc_u_slot(row, col);
-      if (bs >= 0) blk[bs] = (double)val;
+      if (bs >= 0) blk[bs] = (double)val * (col < 6 ? isp * isp : isp);  // V: pose x pose, W: pose x intrinsics
       if (us >= 0) upart[us] += (double)val;  // one owner lane per slot within the warp
     }
   }

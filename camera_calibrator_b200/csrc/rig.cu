@@ -11,8 +11,8 @@
 // Layout: the host sorts the observations of every frame by camera (stable) so
 // that a (frame, camera) SEGMENT is contiguous; a warp pair owns a frame and
 // walks its segments: warp A accumulates V_f(21) and U_cc(21), warp B W_fc(36),
-// g_f(6), g_c(6).  Up to kMaxCams cameras (6C+1 columns fit one warp in the
-// elimination kernel).
+// g_f(6), g_c(6).  Up to kMaxCams cameras (the reference has no bound, extrinsics_calibrator.cpp:9-17;
+// the reduced system is dense (6C)^2 and is factored in shared memory, which sets the cap).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -25,12 +25,14 @@
 
 namespace ccg {
 
-constexpr int kMaxCams = 5;
-constexpr int kMaxN6 = 6 * kMaxCams;          // 30 reduced unknowns at most
+constexpr int kMaxCams = 16;
+constexpr int kMaxN6 = 6 * kMaxCams;          // 96 reduced unknowns at most
 constexpr int kRigWarps = 8;                  // sweep: 4 frame pairs per CTA
-constexpr int kRigPart = 27 * kMaxCams + 9;   // 144: U_cc 21 + g_c 6 per camera | rho sum | sumsq | g'd | d'Dd | n
-constexpr int kRigSchurWarps = 4;
-constexpr int kRigSchurPart = (kMaxN6 + 1) * kMaxN6 + 2;  // 932: (W'Y | W'z) columns x rows | g'D^-1g | fails
+constexpr int kRigPart = 27 * kMaxCams + 9;   // 441: U_cc 21 + g_c 6 per camera | rho sum | sumsq | g'd | d'Dd | n
+constexpr int kRigSchurCols = (kMaxN6 + 1 + 31) / 32;  // columns of [W | g_f] a lane of the elimination kernel owns
+// elimination partial of an item, sized by the actual camera count: (6C + 1) columns x 6C rows of (W'Y | W'z),
+// then g'D^-1g and the failure count
+__host__ __device__ inline int rig_schur_part(int n6) { return (n6 + 1) * n6 + 2; }
 
 struct RigState {
   LmState lm;
@@ -58,6 +60,7 @@ struct RigDev {
   RigState* ps;
   int* n_done;
   int n_cams, blk_stride, yz_stride;
+  int schur_stride;  // rig_schur_part(6 n_cams)
 };
 
 // 2 (y x m)
@@ -311,15 +314,20 @@ k_rig_sweep(RigDev d, double huber_a, double* __restrict__ res_out, double* __re
 }
 
 // --------------------------------------------------------------------------
-// frame elimination, one warp per frame, lane j = column j of [W | g_f]
+// frame elimination, one warp per frame; a lane owns the columns lane, lane + 32, ... of [W | g_f]
+// (6C + 1 columns).  The frame's columns are staged in shared memory so that every lane can read
+// column i for the products (W'Y)[i][j]; the warp's share of the reduced system accumulates in
+// shared memory (dynamic: warps x ((6C + 1) 6C + 2) doubles - 7.4 KB per warp at 5 cameras, 74.5 KB
+// at 16), in a fixed order, so the sums are bit-reproducible.
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRigSchurWarps * 32) k_rig_schur(RigDev d, LmParams P) {
-  __shared__ double s_part[kRigSchurWarps][kRigSchurPart];
+__global__ void k_rig_schur(RigDev d, LmParams P) {
+  extern __shared__ double s_dyn[];
   __shared__ int s_meta[2];
   __shared__ double s_lambda;
   const WorkItem it = d.items[blockIdx.x];
   RigState& ps = d.ps[0];
-  const int C = d.n_cams, n6 = 6 * C;
+  const int C = d.n_cams, n6 = 6 * C, ncol = n6 + 1, part = d.schur_stride;
+  const int nwarps = blockDim.x >> 5;
   if (threadIdx.x == 0) {
     s_meta[0] = ps.lm.par;
     s_meta[1] = (ps.lm.status == 0 || ps.lm.finalize) ? 1 : 0;
@@ -330,11 +338,11 @@ __global__ void __launch_bounds__(kRigSchurWarps * 32) k_rig_schur(RigDev d, LmP
   const int par = s_meta[0];
   const double lambda = s_lambda;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double acc[kMaxN6];
-#pragma unroll
-  for (int j = 0; j < kMaxN6; ++j) acc[j] = 0.0;
+  double* s_acc = s_dyn + (size_t)warp * part;                           // this warp's partial
+  double* s_col = s_dyn + (size_t)nwarps * part + (size_t)warp * 6 * ncol;  // the frame's [W | g_f], row a at a * ncol
+  for (int i = lane; i < part; i += 32) s_acc[i] = 0.0;
   double gDg = 0.0, fails = 0.0;
-  for (int64_t f = it.v0 + warp; f < it.v1; f += kRigSchurWarps) {
+  for (int64_t f = it.v0 + warp; f < it.v1; f += nwarps) {
     const double* blk = d.blk[par] + (size_t)f * d.blk_stride;
     double A[6][6], Dv[6], gv[6];
     {
@@ -356,51 +364,63 @@ __global__ void __launch_bounds__(kRigSchurWarps * 32) k_rig_schur(RigDev d, LmP
     }
     const bool ok = chol6(A);
     if (!ok && lane == 0) fails += 1.0;
-    double col[6], y[6];
+    __syncwarp();  // the previous frame's columns are no longer being read
+    double y[kRigSchurCols][6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double w = 0.0;
-      if (lane < n6) w = blk[27 + a * n6 + lane];
-      else if (lane == n6) w = gv[a];
-      col[a] = w;
-      y[a] = w;
-    }
-    chol6_solve(A, y);
-    double* yz = d.yz + (size_t)f * d.yz_stride;
-    if (lane < n6) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a) yz[a * n6 + lane] = y[a];
-    } else if (lane == n6) {
+    for (int cc = 0; cc < kRigSchurCols; ++cc) {
+      const int j = lane + 32 * cc;
+      double col[6];
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        yz[6 * n6 + a] = y[a];
-        yz[6 * n6 + 6 + a] = gv[a];
-        yz[6 * n6 + 12 + a] = Dv[a];
+        double w = 0.0;
+        if (j < n6) w = blk[27 + a * n6 + j];
+        else if (j == n6) w = gv[a];
+        col[a] = w;
+        y[cc][a] = w;
+        if (j < ncol) s_col[a * ncol + j] = w;
+      }
+      if (j < ncol) chol6_solve(A, y[cc]);
+    }
+    double* yz = d.yz + (size_t)f * d.yz_stride;
+#pragma unroll
+    for (int cc = 0; cc < kRigSchurCols; ++cc) {
+      const int j = lane + 32 * cc;
+      if (j < n6) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) yz[a * n6 + j] = y[cc][a];
+      } else if (j == n6) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          yz[6 * n6 + a] = y[cc][a];
+          yz[6 * n6 + 6 + a] = gv[a];
+          yz[6 * n6 + 12 + a] = Dv[a];
+        }
       }
     }
+    __syncwarp();
+    // (W'Y)[i][j] = sum_a W[a][i] Y[a][j]: this lane's columns j, every row i
 #pragma unroll
-    for (int j = 0; j < kMaxN6; ++j) {
-      double s = 0.0;
+    for (int cc = 0; cc < kRigSchurCols; ++cc) {
+      const int j = lane + 32 * cc;
+      if (j < ncol) {
+        for (int i = 0; i < n6; ++i) {
+          double sum = 0.0;
 #pragma unroll
-      for (int a = 0; a < 6; ++a) s = fma(__shfl_sync(0xffffffffu, col[a], j), y[a], s);
-      if (j < n6) acc[j] += s;
+          for (int a = 0; a < 6; ++a) sum = fma(s_col[a * ncol + i], y[cc][a], sum);
+          s_acc[j * n6 + i] += sum;
+        }
+      }
     }
   }
-  if (lane <= n6) {
-#pragma unroll
-    for (int j = 0; j < kMaxN6; ++j) s_part[warp][lane * kMaxN6 + j] = acc[j];
-  }
   if (lane == 0) {
-    s_part[warp][kRigSchurPart - 2] = gDg;
-    s_part[warp][kRigSchurPart - 1] = fails;
+    s_acc[part - 2] = gDg;
+    s_acc[part - 1] = fails;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < kRigSchurPart; c += blockDim.x) {
-    const int k = c / kMaxN6;
-    double s = 0.0;
-    if (k <= n6 || c >= kRigSchurPart - 2)
-      for (int w = 0; w < kRigSchurWarps; ++w) s += s_part[w][c];
-    d.schur_part[(size_t)blockIdx.x * kRigSchurPart + c] = s;
+  for (int c = threadIdx.x; c < part; c += blockDim.x) {
+    double sum = 0.0;
+    for (int w = 0; w < nwarps; ++w) sum += s_dyn[(size_t)w * part + c];
+    d.schur_part[(size_t)blockIdx.x * part + c] = sum;
   }
 }
 
@@ -453,21 +473,22 @@ __global__ void __launch_bounds__(256) k_rig_decide(RigDev d, LmParams P) {
   }
 }
 
-// reduced (6C x 6C) solve, block-cooperative Cholesky in shared memory
+// reduced (6C x 6C) solve, block-cooperative Cholesky and substitutions in (dynamic) shared memory:
+// S n x n | rhs n | Du n doubles, n = 6C <= 96
 __global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
-  __shared__ double s_buf[kRigSchurPart];
-  __shared__ double S[kMaxN6 * kMaxN6];
-  __shared__ double rhs[kMaxN6], Du[kMaxN6];
+  extern __shared__ double s_dyn[];
   __shared__ int s_flag[2];
+  __shared__ double s_piv;
   RigState& ps = d.ps[0];
   if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
-  for (int c = threadIdx.x; c < kRigSchurPart; c += blockDim.x) s_buf[c] = d.red_schur[c];
-  __syncthreads();
   LmState& s = ps.lm;
-  const int C = ps.n_cams, n = 6 * C, par = s.par;
-  const double* r = s_buf;
+  const int C = ps.n_cams, n = 6 * C, par = s.par, part = d.schur_stride;
+  double* S = s_dyn;
+  double* rhs = S + n * n;
+  double* Du = rhs + n;
+  const double* r = d.red_schur;  // (W'Y | W'z): column j at j * n, then g'D^-1g and the failure count
   if (threadIdx.x == 0) {
-    double gDg = r[kRigSchurPart - 2];
+    double gDg = r[part - 2];
     for (int c = 0; c < C; ++c) {
       if (ps.frozen[c]) continue;
       int idx = 0;
@@ -488,7 +509,7 @@ __global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
       go = 0;
     } else {
       s.iterations++;
-      if (r[kRigSchurPart - 1] > 0.0) {
+      if (r[part - 1] > 0.0) {
         s.solve_ok = 0;
         go = 0;
       }
@@ -503,7 +524,7 @@ __global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int a = e / n, b = e - n * a;
     const int lo = a <= b ? a : b, hi = a <= b ? b : a;
-    double val = -r[hi * kMaxN6 + lo];  // (W'Y)[lo][hi] lives in column hi, row lo
+    double val = -r[hi * n + lo];  // (W'Y)[lo][hi] lives in column hi, row lo
     const int ca = a / 6, cb = b / 6;
     if (ca == cb) {
       const int i = lo - 6 * ca, j = hi - 6 * ca;
@@ -516,7 +537,7 @@ __global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
     const int c = a / 6, i = a - 6 * c;
     const double dd = ps.Ucc[c][i * 6 - i * (i - 1) / 2];
     Du[a] = clampd(dd, P.min_diagonal, P.max_diagonal);
-    rhs[a] = -ps.gc[c][i] + r[n * kMaxN6 + a];
+    rhs[a] = -ps.gc[c][i] + r[n * n + a];
     S[a * n + a] += lambda * Du[a];
   }
   __syncthreads();
@@ -546,21 +567,32 @@ __global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
     }
     __syncthreads();
   }
-  if (threadIdx.x != 0) return;
   if (!s_flag[1]) {
-    s.solve_ok = 0;
+    if (threadIdx.x == 0) s.solve_ok = 0;
     return;
   }
+  // forward L y = rhs and backward L' x = y, column-oriented: thread 0 finishes unknown i, all threads update the rest
   for (int i = 0; i < n; ++i) {
-    double acc = rhs[i];
-    for (int k = 0; k < i; ++k) acc -= S[i * n + k] * rhs[k];
-    rhs[i] = acc / S[i * n + i];
+    if (threadIdx.x == 0) {
+      s_piv = rhs[i] / S[i * n + i];
+      rhs[i] = s_piv;
+    }
+    __syncthreads();
+    const double xi = s_piv;
+    for (int k = i + 1 + threadIdx.x; k < n; k += blockDim.x) rhs[k] -= S[k * n + i] * xi;
+    __syncthreads();
   }
   for (int i = n - 1; i >= 0; --i) {
-    double acc = rhs[i];
-    for (int k = i + 1; k < n; ++k) acc -= S[k * n + i] * rhs[k];
-    rhs[i] = acc / S[i * n + i];
+    if (threadIdx.x == 0) {
+      s_piv = rhs[i] / S[i * n + i];
+      rhs[i] = s_piv;
+    }
+    __syncthreads();
+    const double xi = s_piv;
+    for (int k = threadIdx.x; k < i; k += blockDim.x) rhs[k] -= S[i * n + k] * xi;
+    __syncthreads();
   }
+  if (threadIdx.x != 0) return;
   double gTd = 0.0, dDd = 0.0;
   for (int c = 0; c < C; ++c) {
     double dc[6];
@@ -626,6 +658,8 @@ struct ccg_rig_problem {
   LmParams graph_params;
   int graph_kernels = 0, graph_allreduces = 0;
   bool one_shot = false;                     // created by ccg_rig_solve: runs once, no graph instantiation
+  int schur_warps = 4;                       // elimination kernel: warps per CTA and dynamic shared memory
+  size_t schur_smem = 0, solve_smem = 0;     // (sized by the camera count, rig_build)
 };
 
 namespace {
@@ -709,6 +743,7 @@ int rig_build(ccg_ctx* ctx, const float* u, const float* v, const int32_t* obs_c
   RigDev& d = p->dev;
   std::memset(&d, 0, sizeof(d));
   d.n_cams = C;
+  d.schur_stride = rig_schur_part(6 * C);
   d.blk_stride = ((27 + 36 * C) + 3) / 4 * 4;
   d.yz_stride = ((36 * C + 18) + 3) / 4 * 4;
   float *du_ = nullptr, *dv_ = nullptr, *dX = nullptr;
@@ -728,9 +763,9 @@ int rig_build(ccg_ctx* ctx, const float* u, const float* v, const int32_t* obs_c
   CCG_TRY(rig_alloc(p, &d.blk[1], (size_t)n_frames * d.blk_stride));
   CCG_TRY(rig_alloc(p, &d.yz, (size_t)n_frames * d.yz_stride));
   CCG_TRY(rig_alloc(p, &d.sweep_part, items.size() * kRigPart));
-  CCG_TRY(rig_alloc(p, &d.schur_part, items.size() * kRigSchurPart));
+  CCG_TRY(rig_alloc(p, &d.schur_part, items.size() * (size_t)d.schur_stride));
   CCG_TRY(rig_alloc(p, &d.red_sweep, (size_t)kRigPart));
-  CCG_TRY(rig_alloc(p, &d.red_schur, (size_t)kRigSchurPart));
+  CCG_TRY(rig_alloc(p, &d.red_schur, (size_t)d.schur_stride));
   CCG_TRY(rig_alloc(p, &d.ps, (size_t)1));
   CCG_TRY(rig_alloc(p, &d.n_done, (size_t)1));
   CCG_TRY(rig_alloc(p, &p->d_cam0, (size_t)kMaxCams * 8));
@@ -763,6 +798,25 @@ int rig_build(ccg_ctx* ctx, const float* u, const float* v, const int32_t* obs_c
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_cam0, cam.data(), sizeof(double) * cam.size(), cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(p->d_frozen, frozen.data(), sizeof(int) * kMaxCams, cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaStreamSynchronize(st));
+  // a partitioned rig: the scale feeds the accept/reject thresholds of lm_decide - every rank needs the global maximum
+  if (shared && ctx->world > 1) {
+    double* d_ms = nullptr;
+    CCG_TRY(rig_alloc(p, &d_ms, (size_t)1));
+    CCG_CUDA(ctx, cudaMemcpyAsync(d_ms, &p->meas_scale, sizeof(double), cudaMemcpyHostToDevice, st));
+    CCG_TRY(nccl_allreduce_max(ctx, d_ms, 1));
+    CCG_CUDA(ctx, cudaMemcpyAsync(&p->meas_scale, d_ms, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CCG_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  // dynamic shared memory of the elimination and reduced-solve kernels (opt-in above 48 KB, per device)
+  {
+    const size_t part = (size_t)d.schur_stride, cols = (size_t)6 * (6 * C + 1);
+    p->schur_warps = 4;
+    while (p->schur_warps > 1 && sizeof(double) * p->schur_warps * (part + cols) > 200 * 1024) p->schur_warps /= 2;
+    p->schur_smem = sizeof(double) * p->schur_warps * (part + cols);
+    p->solve_smem = sizeof(double) * ((size_t)36 * C * C + 12 * C);
+    CCG_CUDA(ctx, cudaFuncSetAttribute(k_rig_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->schur_smem));
+    CCG_CUDA(ctx, cudaFuncSetAttribute(k_rig_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->solve_smem));
+  }
   return CCG_OK;
 }
 
@@ -804,16 +858,16 @@ int rig_schur_solve(ccg_rig_problem* p, const LmParams& P, Profiler& prof, int* 
   RigDev& d = p->dev;
   cudaStream_t st = ctx->stream;
   prof.begin(TAG_SCHUR);
-  k_rig_schur<<<p->n_items, kRigSchurWarps * 32, 0, st>>>(d, P);
+  k_rig_schur<<<p->n_items, p->schur_warps * 32, p->schur_smem, st>>>(d, P);
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
-  k_rig_reduce<<<(kRigSchurPart + 31) / 32, 256, 0, st>>>(d.schur_part, kRigSchurPart, p->n_items, d.red_schur);
+  k_rig_reduce<<<(d.schur_stride + 31) / 32, 256, 0, st>>>(d.schur_part, d.schur_stride, p->n_items, d.red_schur);
   if (p->shared && ctx->world > 1) {
-    CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, kRigSchurPart));
+    CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, (size_t)d.schur_stride));
     (*nar)++;
   }
-  k_rig_solve<<<1, 256, 0, st>>>(d, P);
+  k_rig_solve<<<1, 256, p->solve_smem, st>>>(d, P);
   ctx->launches += 2;
   prof.end();
   return CCG_OK;
@@ -972,7 +1026,7 @@ int ccg_rig_create(ccg_ctx* ctx, const float* u, const float* v, const int32_t* 
   if (rig_bad(u, v, obs_cam, obs_point, frame_offsets, n_frames, Xw, n_points, n_cams) || !q_c || !t_c ||
       (n_frames > 0 && (!q_f || !t_f)))
     return set_error(ctx, CCG_ERR_BAD_ARG, "ccg_rig_create: bad argument");
-  if (n_cams > kMaxCams) return set_error(ctx, CCG_ERR_UNSUPPORTED, "at most 5 cameras per rig in this build");
+  if (n_cams > kMaxCams) return set_error(ctx, CCG_ERR_UNSUPPORTED, "at most 16 cameras per rig in this build");
   CCG_CUDA(ctx, cudaSetDevice(ctx->device));
   ccg_rig_problem* p = new ccg_rig_problem();
   const int rc = rig_build(ctx, u, v, obs_cam, obs_point, frame_offsets, n_frames, Xw, n_points, n_cams, q_c,

@@ -131,6 +131,9 @@ void Calibrator::Estimate(const std::vector<Points2D>& in_img_points,
   if (rc != CCG_OK)
     throw std::runtime_error(std::string("Calibrator::Estimate: ") + ccg_status_string(rc) + " " +
                              ccg_last_error(ctx));
+  // the reference overwrites the whole matrix here (K_ = EstimateKFromHomographies(Hs): zero skew, last row
+  // 0 0 1, calibrator.cpp:56) - an earlier SetK with other entries must not survive
+  K_ = Matrix3::Identity();
   StoreResult(ToReport(rep), intr, q.data(), t.data(), n_img);
 }
 
@@ -158,6 +161,7 @@ void Calibrator::EstimateOpenCv(const std::vector<Points2D>& in_img_points,
   if (rc != CCG_OK)
     throw std::runtime_error(std::string("Calibrator::EstimateOpenCv: ") + ccg_status_string(rc) + " " +
                              ccg_last_error(ctx));
+  K_ = Matrix3::Identity();  // the reference assigns OpenCV's whole camera matrix (calibrator.cpp:41)
   StoreResult(ToReport(rep), intr, q.data(), t.data(), n_img);
 }
 

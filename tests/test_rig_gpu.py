@@ -79,10 +79,26 @@ def test_rig_observation_order_is_preserved(ctx):
         assert abs(ga[4][i] - gb[4][j]) <= 1e-9 * max(ga[4][i], 1e-12)
 
 
+def test_rig_twelve_cameras(ctx):
+    """A 12-camera rig (the reference places no bound on the camera count, extrinsics_calibrator.cpp:9-17;
+    system_calibration.py:373-377 adds one per physical camera): 72 x 72 reduced system."""
+    s = synth.rig_scene(n_cams=12, n_frames=60, grid=(5, 4), seed=7, outlier_fraction=0.03)
+    g = rig_api.rig_eval(ctx, *_args(s), s.q_c, s.t_c, s.q_f, s.t_f, HUBER)
+    r = oracle.rig_eval(*_args(s), s.q_c, s.t_c, s.q_f, s.t_f, HUBER)
+    assert abs(g["cost"] - r["cost"]) <= 1e-12 * r["cost"]
+    assert block_err(g["U"], r["U"]) <= 1e-11 and block_err(g["gu"], r["gu"]) <= 1e-10
+    for f in range(60):
+        assert block_err(g["W"][f], r["W"][f]) <= 1e-10, f
+    got = rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    ref = oracle.rig_solve(*_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    _check(got, ref, s)
+
+
 def test_rig_too_many_cameras_is_reported(ctx):
+    """More than 16 cameras: the dense reduced system no longer fits the shared-memory factorisation."""
     import camera_calibrator_b200 as cc
 
-    s = synth.rig_scene(n_cams=6, n_frames=4, grid=(2, 2), seed=1)
+    s = synth.rig_scene(n_cams=17, n_frames=4, grid=(2, 2), seed=1)
     with pytest.raises(cc.CcgError) as e:
         rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
     assert e.value.status == -5
