@@ -343,11 +343,12 @@ __device__ inline void peer_allreduce64(double* s_vals, const PeerComm& pc) {
   if (tid < kPeerVals) {
     const double val = s_vals[tid];
     for (int p = 0; p < pc.world; ++p) pc.box[p][par * kPeerMaxWorld + pc.rank].data[tid] = val;
-    __threadfence_system();
   }
   __syncthreads();
   if (tid < pc.world) {
-    // release: the data stores of the whole CTA are ordered before the flag by the fence + barrier
+    // release: the barrier orders the CTA's data stores before this thread, its system-scope fence (cumulative)
+    // before the flag - one fence per destination instead of one per value
+    __threadfence_system();
     unsigned long long* flag = &pc.box[tid][par * kPeerMaxWorld + pc.rank].seq;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
     // acquire: wait for source rank `tid` in my own mailbox
@@ -462,35 +463,6 @@ __device__ __forceinline__ void chol6_solve(const double (&L)[6][6], double (&b)
 #pragma unroll
     for (int k = i + 1; k < 6; ++k) s -= L[k][i] * b[k];
     b[i] = s / L[i][i];
-  }
-}
-
-// Dense Cholesky solve for the small reduced system (n <= 96), one thread.
-__device__ inline bool chol_dense(double* A, int n) {
-  for (int j = 0; j < n; ++j) {
-    double d = A[j * n + j];
-    for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
-    if (!(d > 0.0) || !isfinite(d)) return false;
-    d = sqrt(d);
-    A[j * n + j] = d;
-    for (int i = j + 1; i < n; ++i) {
-      double s = A[i * n + j];
-      for (int k = 0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
-      A[i * n + j] = s / d;
-    }
-  }
-  return true;
-}
-__device__ inline void chol_dense_solve(const double* L, int n, double* b) {
-  for (int i = 0; i < n; ++i) {
-    double s = b[i];
-    for (int k = 0; k < i; ++k) s -= L[i * n + k] * b[k];
-    b[i] = s / L[i * n + i];
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = b[i];
-    for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * b[k];
-    b[i] = s / L[i * n + i];
   }
 }
 

@@ -573,23 +573,6 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_reduce_schur(Intr
   if (threadIdx.x < kSchurPart) d.red_schur[(size_t)blockIdx.x * kSchurPart + threadIdx.x] = s_buf[threadIdx.x];
 }
 
-// unpack the reduced sweep partial into the full symmetric 9x9 U and g_u
-__device__ inline void unpack_U(const double* r, double* U, double* gu) {
-  for (int i = 0; i < 81; ++i) U[i] = 0.0;
-  auto set = [&](int a, int b, double v) { U[a * 9 + b] = v; U[b * 9 + a] = v; };
-  set(0, 0, r[1]); set(0, 2, r[2]); set(2, 2, r[3]);
-  set(1, 1, r[4]); set(1, 3, r[5]); set(3, 3, r[6]);
-  int idx = 45;
-  for (int c = 0; c < 5; ++c) {
-    set(0, 4 + c, r[25 + c]);
-    set(2, 4 + c, r[30 + c]);
-    set(1, 4 + c, r[35 + c]);
-    set(3, 4 + c, r[40 + c]);
-    for (int e = c; e < 5; ++e) set(4 + c, 4 + e, r[idx++]);
-  }
-  for (int i = 0; i < 9; ++i) gu[i] = r[16 + i];
-}
-
 // index into the reduced sweep partial of U(a, b), a <= b (layout at the top of the file), or -1: structural zero
 __device__ __forceinline__ int u_partial_index(int a, int b) {
   if (b < 4) {
@@ -673,83 +656,6 @@ __global__ void __launch_bounds__(kRedSeg * kSweepPart) k_intr_decide(IntrDev d,
   __shared__ double s_buf[kRedSeg * kSweepPart];
   if (d.ps[blockIdx.x].lm.status != 0) return;
   decide_tail<REDUCE>(d, P, pc, blockIdx.x, s_buf);
-}
-
-// accept / reject for one problem, given its reduced sweep partial r (one thread; batches of small problems)
-__device__ inline void decide_body(IntrState& ps, const LmParams& P, bool evaluated, const double* r, int* n_done) {
-  LmState& s = ps.lm;
-  if (!evaluated) {
-    // the linear solve failed (non-PD): shrink the trust region and retry
-    lm_reject(s, P, n_done);
-    s.solve_ok = 1;
-    if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, n_done, true);
-    return;
-  }
-  const double cost_c = 0.5 * r[0];
-  const bool accept = lm_decide(s, P, cost_c, r[7] + s.gTd_u, r[8] + s.dDd_u, n_done);
-  if (accept) {
-    unpack_U(r, ps.U, ps.gu);
-    s.n_obs = r[3];
-    s.sumsq = r[0];
-  }
-}
-
-// reduced 9x9 solve for one problem, given its reduced elimination partial r (one thread; batches of small problems)
-__device__ inline void solve_body(IntrState& ps, const LmParams& P, const double* r, int* n_done) {
-  LmState& s = ps.lm;
-  const unsigned mask = ps.mask;
-  const int par = s.par;
-  double gDg = r[54];
-  for (int k = 0; k < 9; ++k)
-    if (!((mask >> k) & 1u) && ps.U[k * 9 + k] > 0.0) gDg += ps.gu[k] * ps.gu[k] / ps.U[k * 9 + k];
-  const double rnorm = sqrt(2.0 * s.cost);
-  s.grad_norm = rnorm > 0.0 ? sqrt(gDg) / rnorm : 0.0;
-  if (s.finalize) {
-    s.finalize = 0;
-    return;
-  }
-  if (s.cost == 0.0 || sqrt(gDg) <= P.gradient_tolerance * rnorm) {
-    lm_finish(s, 1, n_done, false);
-    return;
-  }
-  s.iterations++;
-  if (r[55] > 0.0) {
-    s.solve_ok = 0;
-    return;
-  }
-  double S[81], rhs[9], Du[9];
-  const double lambda = s.lambda;
-  for (int a = 0; a < 9; ++a) {
-    Du[a] = clampd(ps.U[a * 9 + a], P.min_diagonal, P.max_diagonal);
-    rhs[a] = -ps.gu[a] + r[45 + a];
-    for (int b = 0; b < 9; ++b) {
-      const double wy = a <= b ? r[up9(a, b)] : r[up9(b, a)];  // packed upper triangle of W'V'^-1W
-      S[a * 9 + b] = ps.U[a * 9 + b] - wy;
-    }
-    S[a * 9 + a] += lambda * Du[a];
-  }
-  for (int k = 0; k < 9; ++k)
-    if ((mask >> k) & 1u) {
-      for (int b = 0; b < 9; ++b) S[k * 9 + b] = S[b * 9 + k] = 0.0;
-      S[k * 9 + k] = 1.0;
-      rhs[k] = 0.0;
-    }
-  if (!chol_dense(S, 9)) {
-    s.solve_ok = 0;
-    return;
-  }
-  chol_dense_solve(S, 9, rhs);
-  double gTd = 0.0, dDd = 0.0;
-  for (int k = 0; k < 9; ++k) {
-    const double dk = ((mask >> k) & 1u) ? 0.0 : rhs[k];
-    ps.du[k] = dk;
-    ps.intr[par ^ 1][k] = ps.intr[par][k] + dk;
-    gTd += ps.gu[k] * dk;
-    dDd += dk * dk * Du[k];
-  }
-  s.gTd_u = gTd;
-  s.dDd_u = dDd;
-  s.solve_ok = 1;
 }
 
 // Reduced 9x9 solve, one CTA per problem (k_intr_solve; REDUCE as in decide_tail).  Also evaluates the gradient norm at the current point.  State
@@ -859,32 +765,6 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
   __shared__ double s_buf[kRedSeg * kSchurPart];
   if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
   solve_tail<REDUCE>(d, P, pc, blockIdx.x, s_buf);
-}
-
-// Batches of small problems (every problem is a single work item): one THREAD per problem
-// instead of one CTA - 4096 reduced solves are 4096 threads, not 4096 mostly idle CTAs.
-constexpr int kBatchThreads = 64;
-__global__ void __launch_bounds__(kBatchThreads) k_intr_decide_batch(IntrDev d, LmParams P, int n_problems) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_problems) return;
-  IntrState& ps = d.ps[b];
-  if (ps.lm.status != 0) return;
-  decide_body(ps, P, ps.lm.solve_ok != 0, d.sweep_part + (size_t)ps.item0 * kSweepPart, d.n_done);
-}
-
-__global__ void __launch_bounds__(kBatchThreads) k_intr_solve_batch(IntrDev d, LmParams P, int n_problems) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_problems) return;
-  IntrState& ps = d.ps[b];
-  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
-  double r[kSchurPart];
-  const double* part = d.schur_part + (size_t)ps.item0 * d.schur_split * kSchurPart;
-  for (int c = 0; c < kSchurPart; ++c) {
-    double acc = 0.0;
-    for (int i = 0; i < d.schur_split; ++i) acc += part[(size_t)i * kSchurPart + c];
-    r[c] = acc;
-  }
-  solve_body(ps, P, r, d.n_done);
 }
 
 // max |measurement| per problem (scale of the cost's rounding noise, lm_decide): one CTA per work
@@ -1224,7 +1104,8 @@ int launch_sweep_decide(ccg_intr_problem* p, const LmParams& P, Profiler& prof, 
     k_intr_decide<0><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P, pc);
     ctx->launches += 2;
   } else if (p->single_item) {
-    k_intr_decide_batch<<<(nb + kBatchThreads - 1) / kBatchThreads, kBatchThreads, 0, st>>>(d, P, nb);
+    // batch of small problems (one work item each): a 64-thread CTA per problem
+    k_intr_decide<1><<<nb, kSweepPart, 0, st>>>(d, P, pc);
     ctx->launches++;
   } else {
     k_intr_decide<1><<<nb, kRedSeg * kSweepPart, 0, st>>>(d, P, pc);
@@ -1257,7 +1138,7 @@ int launch_schur_solve(ccg_intr_problem* p, const LmParams& P, Profiler& prof, i
     k_intr_solve<0><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P, pc);
     ctx->launches += 2;
   } else if (p->single_item) {
-    k_intr_solve_batch<<<(nb + kBatchThreads - 1) / kBatchThreads, kBatchThreads, 0, st>>>(d, P, nb);
+    k_intr_solve<1><<<nb, kSchurPart, 0, st>>>(d, P, pc);
     ctx->launches++;
   } else {
     k_intr_solve<1><<<nb, kRedSeg * kSchurPart, 0, st>>>(d, P, pc);
