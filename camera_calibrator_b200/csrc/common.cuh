@@ -44,6 +44,7 @@ struct ccg_ctx {
   cudaMemPool_t pool = nullptr;
   // per-device opt-in of the default sweep's dynamic shared memory ([RES variant])
   bool sweep_attr[2] = {false, false};
+  bool lm_attr = false;              // the same for the persistent LM kernel
 };
 
 namespace ccg {
@@ -466,6 +467,33 @@ __device__ __forceinline__ void chol6_solve(const double (&L)[6][6], double (&b)
   }
 }
 
+// sin and cos without the out-of-line argument-reduction routine of the CUDA math library (a function call inside
+// a setmaxnreg region makes ptxas drop the register split - and crash): Cody-Waite reduction by pi/2 with three
+// constants (exact for |x| < 1e5; a step angle that large is a rejected step anyway) and the fdlibm kernels on
+// [-pi/4, pi/4], ~1 ulp.
+__device__ __forceinline__ void sincos_inline(double x, double* sn_out, double* cs_out) {
+  const double k = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-k, 1.57079632673412561417e+00, x);
+  r = fma(-k, 6.07710050650619224932e-11, r);
+  r = fma(-k, 2.02226624879595063154e-21, r);
+  const int q = (int)k & 3;
+  const double z = r * r;
+  double sp = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  sp = fma(z, sp, 2.75573137070700676789e-06);
+  sp = fma(z, sp, -1.98412698298579493134e-04);
+  sp = fma(z, sp, 8.33333333332248946124e-03);
+  sp = fma(z, sp, -1.66666666666666324348e-01);
+  const double sn = fma(r * z, sp, r);
+  double cp = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  cp = fma(z, cp, -2.75573143513906633035e-07);
+  cp = fma(z, cp, 2.48015872894767294178e-05);
+  cp = fma(z, cp, -1.38888888888741095749e-03);
+  cp = fma(z, cp, 4.16666666666666019037e-02);
+  const double cs = fma(z * z, cp, fma(-0.5, z, 1.0));
+  *sn_out = (q & 1) ? ((q & 2) ? -cs : cs) : ((q & 2) ? -sn : sn);
+  *cs_out = (q & 1) ? ((q & 2) ? sn : -sn) : ((q & 2) ? -cs : cs);
+}
+
 // [ext] ceres::QuaternionManifold::Plus: x_plus = exp_q(delta) * x, delta = half
 // rotation vector (reference selects it at calibrator.cpp:298,
 // extrinsics_calibrator.cpp:186,196).
@@ -476,7 +504,7 @@ __device__ __forceinline__ void quat_plus(const double (&x)[4], double d0, doubl
   if (n2 > 0.0) {
     const double n = sqrt(n2);
     double sn, cs;
-    sincos(n, &sn, &cs);
+    sincos_inline(n, &sn, &cs);
     qw = cs;
     s = sn / n;
   } else {

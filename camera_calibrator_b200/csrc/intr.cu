@@ -363,6 +363,135 @@ static_assert(kBlk % 2 == 0 && kYz % 2 == 0, "16-byte rows");
 // packed index of (j,k), j <= k, in the 9x9 upper triangle
 __host__ __device__ constexpr int up9(int j, int k) { return j * 9 - j * (j - 1) / 2 + (k - j); }
 
+// One warp eliminates the (up to 32) views base .. base + nv - 1, a lane per view; racc0 / racc1 accumulate the
+// lane's two reduced-system terms (terms L and 32 + L of the 64-value partial).
+__device__ __forceinline__ void schur_warp_pass(const IntrDev& d, const LmParams& P, int par, double lambda, int64_t base,
+                                                int nv, int lane, double& racc0, double& racc1) {
+  const bool has = lane < nv;
+  // (an idle lane computes on a harmless unit block and contributes zeros)
+  double s[kBlk];
+#pragma unroll
+  for (int i = 0; i < kBlk; ++i) s[i] = 0.0;
+  s[0] = s[6] = s[11] = s[15] = s[18] = s[20] = 1.0;
+  if (has) {
+    const double2* src = reinterpret_cast<const double2*>(d.blk[par] + (size_t)(base + lane) * kBlk);
+#pragma unroll
+    for (int i = 0; i < 41; ++i) {
+      const double2 t = src[i];
+      s[2 * i] = t.x;
+      s[2 * i + 1] = t.y;
+    }
+  }
+  double A[6][6], Dv[6], tg[6], gv[6];
+  {
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a; b < 6; ++b) {
+        A[b][a] = s[idx];
+        ++idx;
+      }
+  }
+  double gDg = 0.0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    tg[a] = gv[a] = s[21 + a];
+    Dv[a] = clampd(A[a][a], P.min_diagonal, P.max_diagonal);
+    if (A[a][a] > 0.0) gDg += tg[a] * tg[a] / A[a][a];
+    A[a][a] += lambda * Dv[a];
+  }
+  const bool ok = chol6(A);
+  double T[6][9];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) T[a][c] = s[27 + a * 4 + c];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) T[a][4 + c] = s[51 + a * 5 + c];
+  }
+  // forward substitution: T <- L^-1 W, tg <- L^-1 g_v
+  double inv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) inv[i] = 1.0 / A[i][i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) T[i][c] -= A[i][k] * T[k][c];
+      tg[i] -= A[i][k] * tg[k];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
+    tg[i] *= inv[i];
+  }
+  // reduced-system terms: (W' V'^-1 W)[j][k] = T[:,j].T[:,k] (packed upper, 45), (W' V'^-1 g)[j] = T[:,j].tg (9),
+  // g'D^-1g, failures - summed over the warp's lanes 32 terms at a time (fewer live registers)
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    double vals[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) vals[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+#pragma unroll
+      for (int k = j; k < 9; ++k) {
+        const int e = up9(j, k) - 32 * half;
+        if (e >= 0 && e < 32) {
+          double acc = 0.0;
+#pragma unroll
+          for (int a = 0; a < 6; ++a) acc = fma(T[a][j], T[a][k], acc);
+          vals[e] = acc;
+        }
+      }
+      const int e = 45 + j - 32 * half;
+      if (e >= 0 && e < 32) {
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc = fma(T[a][j], tg[a], acc);
+        vals[e] = acc;
+      }
+    }
+    if (half == 1) {
+      vals[54 - 32] = gDg;
+      vals[55 - 32] = ok ? 0.0 : 1.0;
+    }
+    if (!has) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) vals[i] = 0.0;
+    }
+    const double r = warp_reduce32(vals, lane);
+    if (half == 0) racc0 += r;
+    else racc1 += r;
+  }
+  // backward substitution: Y = L^-T T, z = L^-T tg
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) T[i][c] -= A[k][i] * T[k][c];
+      tg[i] -= A[k][i] * tg[k];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
+    tg[i] *= inv[i];
+  }
+  if (has) {
+    // the elimination record: Y 54 | z 6 | g_v 6 | D_v 6
+    double2* dst = reinterpret_cast<double2*>(d.yz + (size_t)(base + lane) * kYz);
+#pragma unroll
+    for (int i = 0; i < 27; ++i) dst[i] = make_double2(T[(2 * i) / 9][(2 * i) % 9], T[(2 * i + 1) / 9][(2 * i + 1) % 9]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      dst[27 + i] = make_double2(tg[2 * i], tg[2 * i + 1]);
+      dst[30 + i] = make_double2(gv[2 * i], gv[2 * i + 1]);
+      dst[33 + i] = make_double2(Dv[2 * i], Dv[2 * i + 1]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSchurWarps * 32) k_intr_schur(IntrDev d, LmParams P) {
   __shared__ double s_part[kSchurWarps][kSchurPart];
   __shared__ int s_meta[2];
@@ -389,130 +518,7 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_intr_schur(IntrDev d, LmPa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double racc0 = 0.0, racc1 = 0.0;  // lane L: reduced-system terms L and 32+L
   for (int64_t base = it.v0 + warp * 32; base < it.v1; base += kSchurWarps * 32) {
-    const int nv = (int)min((int64_t)32, it.v1 - base);
-    const bool has = lane < nv;
-    // (an idle lane computes on a harmless unit block and contributes zeros)
-    double s[kBlk];
-#pragma unroll
-    for (int i = 0; i < kBlk; ++i) s[i] = 0.0;
-    s[0] = s[6] = s[11] = s[15] = s[18] = s[20] = 1.0;
-    if (has) {
-      const double2* src = reinterpret_cast<const double2*>(d.blk[par] + (size_t)(base + lane) * kBlk);
-#pragma unroll
-      for (int i = 0; i < 41; ++i) {
-        const double2 t = src[i];
-        s[2 * i] = t.x;
-        s[2 * i + 1] = t.y;
-      }
-    }
-    double A[6][6], Dv[6], tg[6], gv[6];
-    {
-      int idx = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = a; b < 6; ++b) {
-          A[b][a] = s[idx];
-          ++idx;
-        }
-    }
-    double gDg = 0.0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      tg[a] = gv[a] = s[21 + a];
-      Dv[a] = clampd(A[a][a], P.min_diagonal, P.max_diagonal);
-      if (A[a][a] > 0.0) gDg += tg[a] * tg[a] / A[a][a];
-      A[a][a] += lambda * Dv[a];
-    }
-    const bool ok = chol6(A);
-    double T[6][9];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) T[a][c] = s[27 + a * 4 + c];
-#pragma unroll
-      for (int c = 0; c < 5; ++c) T[a][4 + c] = s[51 + a * 5 + c];
-    }
-    // forward substitution: T <- L^-1 W, tg <- L^-1 g_v
-    double inv[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) inv[i] = 1.0 / A[i][i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-      for (int k = 0; k < i; ++k) {
-#pragma unroll
-        for (int c = 0; c < 9; ++c) T[i][c] -= A[i][k] * T[k][c];
-        tg[i] -= A[i][k] * tg[k];
-      }
-#pragma unroll
-      for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
-      tg[i] *= inv[i];
-    }
-    // reduced-system terms: (W' V'^-1 W)[j][k] = T[:,j].T[:,k] (packed upper, 45), (W' V'^-1 g)[j] = T[:,j].tg (9),
-    // g'D^-1g, failures - summed over the warp's lanes 32 terms at a time (fewer live registers)
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      double vals[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) vals[i] = 0.0;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-#pragma unroll
-        for (int k = j; k < 9; ++k) {
-          const int e = up9(j, k) - 32 * half;
-          if (e >= 0 && e < 32) {
-            double acc = 0.0;
-#pragma unroll
-            for (int a = 0; a < 6; ++a) acc = fma(T[a][j], T[a][k], acc);
-            vals[e] = acc;
-          }
-        }
-        const int e = 45 + j - 32 * half;
-        if (e >= 0 && e < 32) {
-          double acc = 0.0;
-#pragma unroll
-          for (int a = 0; a < 6; ++a) acc = fma(T[a][j], tg[a], acc);
-          vals[e] = acc;
-        }
-      }
-      if (half == 1) {
-        vals[54 - 32] = gDg;
-        vals[55 - 32] = ok ? 0.0 : 1.0;
-      }
-      if (!has) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) vals[i] = 0.0;
-      }
-      const double r = warp_reduce32(vals, lane);
-      if (half == 0) racc0 += r;
-      else racc1 += r;
-    }
-    // backward substitution: Y = L^-T T, z = L^-T tg
-#pragma unroll
-    for (int i = 5; i >= 0; --i) {
-#pragma unroll
-      for (int k = i + 1; k < 6; ++k) {
-#pragma unroll
-        for (int c = 0; c < 9; ++c) T[i][c] -= A[k][i] * T[k][c];
-        tg[i] -= A[k][i] * tg[k];
-      }
-#pragma unroll
-      for (int c = 0; c < 9; ++c) T[i][c] *= inv[i];
-      tg[i] *= inv[i];
-    }
-    if (has) {
-      // the elimination record: Y 54 | z 6 | g_v 6 | D_v 6
-      double2* dst = reinterpret_cast<double2*>(d.yz + (size_t)(base + lane) * kYz);
-#pragma unroll
-      for (int i = 0; i < 27; ++i) dst[i] = make_double2(T[(2 * i) / 9][(2 * i) % 9], T[(2 * i + 1) / 9][(2 * i + 1) % 9]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        dst[27 + i] = make_double2(tg[2 * i], tg[2 * i + 1]);
-        dst[30 + i] = make_double2(gv[2 * i], gv[2 * i + 1]);
-        dst[33 + i] = make_double2(Dv[2 * i], Dv[2 * i + 1]);
-      }
-    }
+    schur_warp_pass(d, P, par, lambda, base, (int)min((int64_t)32, it.v1 - base), lane, racc0, racc1);
   }
   s_part[warp][lane] = racc0;
   s_part[warp][32 + lane] = racc1;
@@ -767,6 +773,10 @@ __global__ void __launch_bounds__(kRedSeg * kSchurPart) k_intr_solve(IntrDev d, 
   solve_tail<REDUCE>(d, P, pc, blockIdx.x, s_buf);
 }
 
+}  // namespace ccg
+#include "intr_lm.cuh"
+namespace ccg {
+
 // max |measurement| per problem (scale of the cost's rounding noise, lm_decide): one CTA per work
 // item, non-negative floats compared through their bit patterns
 __global__ void __launch_bounds__(256) k_intr_meas_scale(IntrDev d, unsigned* __restrict__ bits) {
@@ -863,6 +873,10 @@ struct ccg_intr_problem {
   ccg_report* d_out_rep = nullptr;
   int64_t* d_problem_off = nullptr;
   bool one_shot = false;             // created by ccg_intrinsics_solve*: runs once, no graph instantiation
+  LmCtl* d_ctl = nullptr;            // persistent LM kernel: grid-barrier counter
+  double* d_lm_schur = nullptr;      // persistent LM kernel: one elimination partial per work item
+  int lm_mode = -1;                  // -1 the multi-launch loop, 0 the whole loop as one launch (k_intr_lm, intr_lm.cuh)
+  int lm_grid = 0;
   int2* d_item_ranges = nullptr;
   float* d_obs = nullptr;
   bool single_item = false;          // every problem is one work item (batch of small problems)
@@ -916,7 +930,8 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   // one CTA per SM for a big problem (255-register kernels: one resident CTA per SM, so more
   // items only add wave-quantisation tail); small problems get one item each
   const int64_t target_items = (int64_t)ctx->sm_count;
-  int64_t vpi = std::max<int64_t>(kWarps / 2, (n_views + target_items - 1) / std::max<int64_t>(target_items, 1));
+  // (at least 32 views per item: four per warp pair of the default sweep; fewer only add CTAs that mostly wait)
+  int64_t vpi = std::max<int64_t>(32, (n_views + target_items - 1) / std::max<int64_t>(target_items, 1));
   std::vector<WorkItem> items;
   std::vector<int2> ranges((size_t)n_problems);
   p->problem_off.assign(problem_offsets, problem_offsets + n_problems + 1);
@@ -1042,6 +1057,26 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
     // a partitioned calibration: the scale feeds the accept/reject thresholds of lm_decide, and every rank
     // must take the same branch - the maximum is over ALL ranks' observations
     if (shared && ctx->world > 1) CCG_TRY(nccl_allreduce_max(ctx, p->d_meas_scale, (size_t)n_problems));
+  }
+  CCG_TRY(dev_alloc(p, &p->d_ctl, (size_t)1));
+  CCG_TRY(dev_alloc(p, &p->d_lm_schur, items.size() * (size_t)kSchurPart));
+  // the whole LM loop as one launch (intr_lm.cuh) when every CTA of the problem can be resident at once (one
+  // problem, one CTA per SM) or when every problem is a single work item (batches of small problems)
+  // Measured (B200): one launch beats the four-launches-per-iteration loop for small problems (C1 0.21 vs 0.34 ms, C2
+  // 0.30 vs 0.40 ms per solve) and loses from a few million observations on (12,500 x 400: 1.20 vs 1.13 ms; C5: 7.07
+  // vs 6.69 ms), where its elimination phase - 8 warps per SM, register-starved next to the sweep's split - costs
+  // more than the launches it saves.  CCG_PERSIST_MAX_OBS overrides the threshold (experiments).
+  p->lm_mode = -1;
+  if (!getenv("CCG_NO_PERSIST")) {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    const char* e = getenv("CCG_PERSIST_MAX_OBS");
+    const int64_t max_obs = e ? atoll(e) : 1500000;
+    if (n_problems == 1 && coop && n_obs <= max_obs && p->n_items <= ctx->sm_count &&
+        (!(shared && ctx->world > 1) || ctx->peer_ok)) {
+      p->lm_mode = 0;
+      p->lm_grid = p->n_items;
+    }
   }
   CCG_CUDA(ctx, cudaStreamSynchronize(st));  // host staging vectors go out of scope
   return CCG_OK;
@@ -1177,6 +1212,46 @@ int run_problem(ccg_intr_problem* p, const ccg_opts& opts, ccg_timing* timing) {
   }
   cudaEventRecord(ctx->events[ev_total0], ctx->stream);
   CCG_TRY(reset_problem(p, P));  // restoring the initial parameters is part of the timed solve
+  if (p->lm_mode >= 0 && P.hessian_fp64 == 0 && !prof.on) {
+    // one launch for the whole loop
+    const bool partitioned = p->shared && ctx->world > 1;
+    if (partitioned) {
+      CCG_TRY(peer_resync(ctx, p->dev.red_sweep));  // lines the ranks up and agrees on the allreduce sequence number
+      n_allreduce++;
+    }
+    CCG_CUDA(ctx, cudaMemsetAsync(p->d_ctl, 0, sizeof(LmCtl), ctx->stream));
+    IntrDev dev = p->dev;
+    LmParams Pk = P;
+    PeerComm pck = peer_comm(ctx);
+    int reduce_mode = partitioned ? 2 : 1;
+    LmCtl* ctl = p->d_ctl;
+    double* lms = p->d_lm_schur;
+    void* args[] = {&dev, &Pk, &pck, &reduce_mode, &ctl, &lms};
+    if (!ctx->lm_attr) {
+      CCG_CUDA(ctx, cudaFuncSetAttribute(k_intr_lm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmem));
+      ctx->lm_attr = true;
+    }
+    CCG_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_intr_lm, dim3(p->lm_grid), dim3(kSwThreads), args, kSwSmem,
+                                              ctx->stream));
+    ctx->launches++;
+    cudaEventRecord(ctx->events[ev_total1], ctx->stream);
+    int counts[2] = {0, 0};  // iterations, sweeps of problem 0: the allreduce count of a partitioned solve
+    if (partitioned)
+      CCG_CUDA(ctx, cudaMemcpyAsync(counts, reinterpret_cast<const char*>(&p->dev.ps->lm) + offsetof(LmState, iterations),
+                                    sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CCG_CUDA(ctx, cudaGetLastError());
+    if (timing) {
+      std::memset(timing, 0, sizeof(*timing));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->events[ev_total0], ctx->events[ev_total1]);
+      timing->total_ms = ms;
+      timing->allreduces = n_allreduce + (partitioned ? 2 * counts[0] + 3 : 0);
+      timing->sweep_obs = p->n_obs;
+      timing->sweep_views = p->n_views;
+    }
+    return CCG_OK;
+  }
   if (p->shared && ctx->world > 1 && ctx->peer_ok) {
     // line the ranks up once per solve with a collective that waits without a deadline; the
     // peer-memory allreduces inside the kernels then only see the skew of one LM iteration

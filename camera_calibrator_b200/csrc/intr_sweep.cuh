@@ -95,7 +95,14 @@ constexpr bool kSwF16 = CCG_SW_F16 != 0;
 constexpr int kTcRow = 20;            // 32-bit words per tile row (16 + 4: conflict-free STS.128 and LDS.64)
 constexpr int kTcTile = (kSwF16 ? 32 : 64) * kTcRow;  // one 32-observation tile: a row per observation (FP16 pairs) or per residual
 
-constexpr size_t kSwSmem = sizeof(double) * kSwWarps * kSweepPart +
+// The Jacobian warp of a pair is the faster one; left alone it runs ahead of its FP64 partner by more than L2 holds
+// (all pairs of the GPU together), and every block is then fetched from HBM twice (measured: 1.70 x the algorithmic
+// bytes).  It therefore never requests a block more than kSwLead blocks beyond the one its partner has consumed.
+#ifndef CCG_SW_LEAD
+#define CCG_SW_LEAD 0
+#endif
+constexpr int kSwLead = CCG_SW_LEAD;
+constexpr size_t kSwSmem = sizeof(int) * 16 + sizeof(double) * kSwWarps * kSweepPart +
                            sizeof(float) * kSwPairs * (kSwStagesD * kSwStageD + kSwStagesJ * kSwStageJ + kSwTiles * kTcTile);
 static_assert(kSwSmem <= 227 * 1024, "shared memory");
 static_assert(kSwTail == 0 || kSwTiles * kTcTile >= kSwStagesD * kSwStageD, "the FP64 tail's ring lives in the tile(s)");
@@ -645,8 +652,8 @@ struct SwObs3 {
 
 // LEAN (the Jacobian warps' share, fewer registers): one chunk at a time, the pose is loaded at the view's start.
 template <bool RES, bool LEAN>
-__device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, const double* s_k, int par, int va, int vb,
-                                            int lane, double* upart, double* __restrict__ res_out) {
+__device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, unsigned pace, const double* s_k, int par,
+                                            int va, int vb, int lane, double* upart, double* __restrict__ res_out) {
   TcConst64 K;
   K.fx = s_k[0]; K.fy = s_k[1]; K.cx = s_k[2]; K.cy = s_k[3];
   K.k1 = s_k[4]; K.k2 = s_k[5]; K.p1 = s_k[6]; K.p2 = s_k[7]; K.k3 = s_k[8];
@@ -662,8 +669,13 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, c
     strm.init(d.obs_blk, vmeta[va].x, vmeta[vb].x, (unsigned)opaque((int)stages), lane);
     // the lane keeps the observations of the next two chunks of its stream in registers (o0: next, o1: the one
     // after): the shared-memory latency of a chunk hides behind the arithmetic of the chunks before it
+    int consumed = 0;  // blocks read so far, published for the partner's pacing
     auto load = [&]() -> SwObs5 {
       const unsigned a = strm.next(lane);
+      if (!LEAN) {
+        ++consumed;
+        if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(pace), "r"(consumed) : "memory");
+      }
       SwObs5 o;
       o.mu = lds_f32(a); o.mv = lds_f32(a + 128); o.X = lds_f32(a + 256); o.Y = lds_f32(a + 384); o.Z = lds_f32(a + 512);
       return o;
@@ -740,6 +752,7 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, c
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
+  if (!LEAN && lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(pace), "r"(0x7fffffff) : "memory");
   // lane-private sums -> the warp's partial: [0] sum r^2 | [16..24] g_u
   double tmp[16];
 #pragma unroll
@@ -757,8 +770,8 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, c
 // The Jacobian + tensor role over the views [va, vb): V, W (into the view blocks) and U (into the
 // warp's partial).  `stages`, `tile` = shared addresses.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, unsigned tile, const double* s_k, int par,
-                                           int va, int vb, int lane, double* upart) {
+__device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, unsigned tile, unsigned pace, const double* s_k,
+                                           int par, int va, int vb, int lane, double* upart) {
   if (va >= vb) return;
   lane = opaque(lane);
   tile = (unsigned)opaque((int)tile);
@@ -776,7 +789,20 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
   double* blk0 = opaque_ptr(d.blk[par ^ 1]);
   SwStream<3, kSwAheadJ> strm;
   strm.init(d.obs_blk, vmeta[va].x, vmeta[vb].x, (unsigned)opaque((int)stages), lane);
+  int requested = 0;
   auto load = [&]() -> SwObs3 {
+    // pacing: stay within kSwLead blocks of the FP64 partner (see kSwLead)
+    ++requested;
+#ifndef CCG_SW_ONLY_J
+    if (kSwLead > 0 && kSwTail == 0) {
+      for (;;) {
+        int seen;
+        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(seen) : "r"(pace) : "memory");
+        if (requested - kSwLead <= seen) break;  // (seen = INT_MAX once the partner is done)
+        __nanosleep(256);
+      }
+    }
+#endif
     const unsigned a = strm.next(lane);
     SwObs3 o;
     o.X = lds_f32(a); o.Y = lds_f32(a + 128); o.Z = lds_f32(a + 256);
@@ -856,15 +882,80 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
 }
 
 // ---------------------------------------------------------------------------------------------
-// The sweep.  One CTA per work item; see the top of the file for the role layout.
+// The sweep of one work item by one CTA (all kSwThreads threads call): candidate poses, then the two
+// roles, then the item's 64-value partial into `out` (global or shared memory).  s_k: intrinsics at the
+// candidate point, s_du: the reduced step (both in shared memory).
 // ---------------------------------------------------------------------------------------------
+struct SwSmem {  // dynamic shared memory of a sweep CTA
+  int* pace;  // per pair: blocks the FP64 warp has consumed (the Jacobian warp's pacing)
+  double (*part)[kSweepPart];
+  float *stage_d, *stage_j, *tiles;
+  __device__ __forceinline__ explicit SwSmem(unsigned char* dyn) {
+    pace = reinterpret_cast<int*>(dyn);
+    dyn += sizeof(int) * 16;
+    part = reinterpret_cast<double(*)[kSweepPart]>(dyn);
+    stage_d = reinterpret_cast<float*>(dyn + sizeof(double) * kSwWarps * kSweepPart);
+    stage_j = stage_d + kSwPairs * kSwStagesD * kSwStageD;
+    tiles = stage_j + kSwPairs * kSwStagesJ * kSwStageJ;
+  }
+};
+
+// ROLE: 0 = the calling CTA's warps take their roles here and split the registers (the sweep as a launch of
+// its own); 1 / 2 = the caller is an FP64 / a Jacobian warp whose registers are already set (the persistent LM
+// kernel instantiates its whole loop once per role, so that no code is shared between the two register budgets).
+template <bool RES, int ROLE>
+__device__ __forceinline__ void sw_sweep_item(const IntrDev& d, const WorkItem& it, int par, const double* s_k,
+                                              const double* s_du, const SwSmem& sm, double (*s_red)[kSwWarps],
+                                              double* s_step, double* out, double* __restrict__ res_out) {
+  for (int i = threadIdx.x; i < kSwWarps * kSweepPart; i += kSwThreads) (&sm.part[0][0])[i] = 0.0;
+  if (threadIdx.x < kSwPairs) sm.pace[threadIdx.x] = 0;
+  sw_candidate_poses(d, it, par, s_du, s_red, s_step);  // (its barrier also covers the zeroing above)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* upart = sm.part[warp];
+  // pair p (Jacobian warp p, FP64 warp kSwPairs + p, same SM sub-partition) owns the p-th part of the item's views
+  const int pair = warp & (kSwPairs - 1), nv = it.v1 - it.v0;
+  const int va = it.v0 + (int)((int64_t)nv * pair / kSwPairs), vb = it.v0 + (int)((int64_t)nv * (pair + 1) / kSwPairs);
+  const int vsplit = va + ((vb - va) * (64 - kSwTail) + 32) / 64;  // FP64 role: [va, vsplit) the FP64 warp, the rest its partner
+  if (ROLE == 1 || (ROLE == 0 && warp >= kSwPairs)) {
+    // =========================== FP64 role ===========================
+    if (ROLE == 0 && kSwRegD > kSwRegLaunch) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSwRegD));
+#ifndef CCG_SW_ONLY_J  // timing experiments: one role alone (results are then incomplete)
+    sw_run_fp64<RES, false>(d, smem_u32(sm.stage_d + pair * kSwStagesD * kSwStageD), smem_u32(sm.pace + pair), s_k, par, va,
+                            vsplit, lane, upart, res_out);
+#endif
+  } else {
+    // =========================== Jacobian + tensor role ===========================
+    if (ROLE == 0 && kSwRegJ < kSwRegLaunch) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSwRegJ));
+#ifndef CCG_SW_ONLY_D
+    sw_run_jac(d, smem_u32(sm.stage_j + pair * kSwStagesJ * kSwStageJ), smem_u32(sm.tiles + pair * kSwTiles * kTcTile),
+               smem_u32(sm.pace + pair), s_k, par, va, vb, lane, upart);
+#endif
+#if !defined(CCG_SW_ONLY_J) || defined(CCG_SW_TAIL_ANYWAY)
+    // the tail of the pair's FP64 work; the ring lives in the tile(s), free by now (every lane is past its last
+    // tile read: sw_run_fp64 synchronises the warp before the first ring write lands)
+    if (kSwTail > 0) {
+      __syncwarp();
+      sw_run_fp64<RES, true>(d, smem_u32(sm.tiles + pair * kSwTiles * kTcTile), 0u, s_k, par, vsplit, vb, lane, upart, res_out);
+    }
+#endif
+  }
+  __syncthreads();
+  if (threadIdx.x < kSweepPart) {  // (Jacobian-role threads: warps 0 and 1)
+    double s = 0.0;
+    if (threadIdx.x == 7 || threadIdx.x == 8) {
+      s = s_step[threadIdx.x - 7];  // the model terms g'd, d'Dd of this item
+    } else {
+#pragma unroll
+      for (int w = 0; w < kSwWarps; ++w) s += sm.part[w][threadIdx.x];
+    }
+    out[threadIdx.x] = s;
+  }
+}
+
+// The sweep as a launch of its own: one CTA per work item, state read from global memory.
 template <bool RES>
 __global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, double* __restrict__ res_out) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  double(*s_part)[kSweepPart] = reinterpret_cast<double(*)[kSweepPart]>(s_dyn);
-  float* s_stage_d = reinterpret_cast<float*>(s_dyn + sizeof(double) * kSwWarps * kSweepPart);
-  float* s_stage_j = s_stage_d + kSwPairs * kSwStagesD * kSwStageD;
-  float* s_tiles = s_stage_j + kSwPairs * kSwStagesJ * kSwStageJ;
   __shared__ double s_k[9], s_du[9], s_step[2];
   __shared__ double s_red[2][kSwWarps];
   __shared__ int s_meta[2];
@@ -876,56 +967,14 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, doub
   }
   __syncthreads();
   if (!s_meta[1]) return;
-  {
-    const int par = s_meta[0];
-    if (threadIdx.x < 9) {
-      s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
-      s_du[threadIdx.x] = ps.du[threadIdx.x];
-    }
-    for (int i = threadIdx.x; i < kSwWarps * kSweepPart; i += kSwThreads) (&s_part[0][0])[i] = 0.0;
-    __syncthreads();
-    sw_candidate_poses(d, it, par, s_du, s_red, s_step);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* upart = s_part[warp];
-    // pair p (Jacobian warp p, FP64 warp kSwPairs + p, same SM sub-partition) owns the p-th part of the item's views
-    const int pair = warp & (kSwPairs - 1), nv = it.v1 - it.v0;
-    const int va = it.v0 + (int)((int64_t)nv * pair / kSwPairs), vb = it.v0 + (int)((int64_t)nv * (pair + 1) / kSwPairs);
-    const int vsplit = va + ((vb - va) * (64 - kSwTail) + 32) / 64;  // FP64 role: [va, vsplit) the FP64 warp, the rest its partner
-    if (warp >= kSwPairs) {
-      // =========================== FP64 role ===========================
-      if (kSwRegD > kSwRegLaunch) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSwRegD));
-#ifndef CCG_SW_ONLY_J  // timing experiments: one role alone (results are then incomplete)
-      sw_run_fp64<RES, false>(d, smem_u32(s_stage_d + pair * kSwStagesD * kSwStageD), s_k, par, va, vsplit, lane, upart,
-                              res_out);
-#endif
-    } else {
-      // =========================== Jacobian + tensor role ===========================
-      if (kSwRegJ < kSwRegLaunch) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSwRegJ));
-#ifndef CCG_SW_ONLY_D
-      sw_run_jac(d, smem_u32(s_stage_j + pair * kSwStagesJ * kSwStageJ), smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k,
-                 par, va, vb, lane, upart);
-#endif
-#if !defined(CCG_SW_ONLY_J) || defined(CCG_SW_TAIL_ANYWAY)
-      // the tail of the pair's FP64 work; the ring lives in the tile(s), free by now (every lane is past its last
-      // tile read: sw_run_fp64 synchronises the warp before the first ring write lands)
-      if (kSwTail > 0) {
-        __syncwarp();
-        sw_run_fp64<RES, true>(d, smem_u32(s_tiles + pair * kSwTiles * kTcTile), s_k, par, vsplit, vb, lane, upart, res_out);
-      }
-#endif
-    }
-    __syncthreads();
-    if (threadIdx.x < kSweepPart) {
-      double s = 0.0;
-      if (threadIdx.x == 7 || threadIdx.x == 8) {
-        s = s_step[threadIdx.x - 7];  // the model terms g'd, d'Dd of this item
-      } else {
-#pragma unroll
-        for (int w = 0; w < kSwWarps; ++w) s += s_part[w][threadIdx.x];
-      }
-      d.sweep_part[(size_t)blockIdx.x * kSweepPart + threadIdx.x] = s;
-    }
+  const int par = s_meta[0];
+  if (threadIdx.x < 9) {
+    s_k[threadIdx.x] = ps.intr[par ^ 1][threadIdx.x];
+    s_du[threadIdx.x] = ps.du[threadIdx.x];
   }
+  __syncthreads();
+  sw_sweep_item<RES, 0>(d, it, par, s_k, s_du, SwSmem(s_dyn), s_red, s_step,
+                            d.sweep_part + (size_t)blockIdx.x * kSweepPart, res_out);
 }
 
 // Observations SoA -> 640-byte blocks of 32 (views padded to whole blocks with zeros); one warp per view.
