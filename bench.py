@@ -46,10 +46,11 @@ WORKLOADS = {
 }
 # per observation per sweep of the default (warp-specialised tensor-core) sweep kernel, from the SASS of the
 # full-chunk loops of its two roles (profiles/r02_sass_opcodes.md, tools/sass_loops.py): FP64 role 54 DFMA + 20 DMUL
-# + 14 DADD, Jacobian role 32 FFMA + 41 FMUL + 15 FADD, and 16 HMMA.1688.TF32 (m16n8k8) per 32 observations
+# + 14 DADD, Jacobian role 32 FFMA + 43 FMUL + 15 FADD, and 8 HMMA.16816.F32 (m16n8k16, FP16 operands, FP32
+# accumulation) per 32 observations
 FP64_FLOP_PER_OBS = 142.0
-FP32_FLOP_PER_OBS = 120.0
-TF32_FLOP_PER_OBS = 16 * 2.0 * 16 * 8 * 8 / 32.0
+FP32_FLOP_PER_OBS = 122.0
+MMA_FLOP_PER_OBS = 8 * 2.0 * 16 * 8 * 16 / 32.0
 
 
 def algorithmic_bytes(n_obs, n_views):
@@ -622,7 +623,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": args.scaling if wl["poff"] is None else "weak",
             "vs_baseline": None,
-            "dtype": "f64 residual/cost/gradient + reduced system; J'J blocks: TF32 tensor-core products of float32 rows",
+            "dtype": "f64 residual/cost/gradient + reduced system; J'J blocks: fp16-operand tensor-core products (fp32 accumulate) of float32 rows",
             "data": "synthetic",
             "config": workload_config(args.workload, world, args.scaling),
             "lm_iterations_per_s": iters / (ms_per_step * 1e-3),
@@ -647,8 +648,8 @@ def run_ours(args):
                                   "peak_source": "DFMA micro-benchmark run in this process"},
                          "fp32": {"achieved_tflops": FP32_FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
                                   "flop_per_obs": FP32_FLOP_PER_OBS},
-                         "tf32_mma": {"achieved_tflops": TF32_FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
-                                      "flop_per_obs": TF32_FLOP_PER_OBS}},
+                         "f16_mma": {"achieved_tflops": MMA_FLOP_PER_OBS * d.n_obs / (sweep_ms_avg * 1e-3) / 1e12,
+                                      "flop_per_obs": MMA_FLOP_PER_OBS}},
             "cpu_baseline": {"value": cpu_v, "unit": "obs/s", "cores": oracle.num_threads(), "kind": "port",
                              "sample": sample[5], "seconds": cpu_dt},
             "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": int(allsum(float(h2d))) if world > 1 else int(h2d),

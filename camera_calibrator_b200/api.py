@@ -139,6 +139,18 @@ class Context:
                                            ptr(py, C.c_float)), "ccg_distort")
         return px, py
 
+    def homography_batch(self, x1, y1, x2, y2, set_offsets):
+        """EstimateHomography (reference geometry.cpp:70-107) for many point sets on the device: (n_sets, 3, 3),
+        unit Frobenius norm; NaN in H[i, 0, 0] marks a degenerate set."""
+        x1, y1, x2, y2 = f32(x1), f32(y1), f32(x2), f32(y2)
+        off = np.ascontiguousarray(set_offsets, dtype=np.int64)
+        n = off.size - 1
+        H = np.zeros((n, 3, 3))
+        self._check(_ccg.lib().ccg_homography_batch(self._h, ptr(x1, C.c_float), ptr(y1, C.c_float), ptr(x2, C.c_float),
+                                                    ptr(y2, C.c_float), ptr(off, C.c_int64), C.c_int64(n),
+                                                    ptr(H, C.c_double)), "ccg_homography_batch")
+        return H
+
     def intrinsics_estimate(self, u, v, X, Y, Z, view_offsets, const_mask=0, opts=None, problem_offsets=None):
         """Calibrator::Estimate: closed-form initialisation on the device + LM solve.
         Returns (intr[9] or [B,9], q[V,4], t[V,3], report(s), intr_init)."""

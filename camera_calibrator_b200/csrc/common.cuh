@@ -37,6 +37,11 @@ struct ccg_ctx {
   bool peer_ok = false;
   // pinned scratch for small D2H polls
   int* h_poll = nullptr;
+  // pinned staging arena for the per-view arrays a problem build uploads (poses, offsets, work items): packed by
+  // the host while the observation arrays are already on the wire, then copied with real asynchronous DMA (a copy from
+  // pageable memory waits for the stream and bounces through the driver's own staging buffer)
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
   // event pool for opts.profile
   std::vector<cudaEvent_t> events;
   // stream-ordered device memory pool: freed problem buffers stay cached for the next solve
@@ -86,6 +91,7 @@ PeerComm peer_comm(const ccg_ctx* ctx);
 
 // device memory from the context's pool, ordered on ctx->stream
 cudaError_t pool_alloc(ccg_ctx* ctx, void** out, size_t bytes);
+void* host_stage(ccg_ctx* ctx, size_t bytes);  // pinned, >= bytes, valid until the next call; nullptr if unavailable
 void pool_free(ccg_ctx* ctx, void* ptr);
 
 // --------------------------------------------------------------------------

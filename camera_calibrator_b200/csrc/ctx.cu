@@ -92,6 +92,22 @@ void pool_free(ccg_ctx* ctx, void* ptr) {
   else cudaFreeAsync(ptr, ctx->stream);
 }
 
+void* host_stage(ccg_ctx* ctx, size_t bytes) {
+  if (bytes > ((size_t)1 << 30)) return nullptr;  // (the caller falls back to pageable staging)
+  if (bytes <= ctx->h_stage_bytes) return ctx->h_stage;
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  ctx->h_stage = nullptr;
+  ctx->h_stage_bytes = 0;
+  const size_t want = std::max<size_t>(bytes + bytes / 4, (size_t)1 << 20);
+  if (cudaMallocHost(&ctx->h_stage, want) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->h_stage = nullptr;
+    return nullptr;
+  }
+  ctx->h_stage_bytes = want;
+  return ctx->h_stage;
+}
+
 // ------------------------------------------------------- peer mailboxes ----
 PeerComm peer_comm(const ccg_ctx* ctx) {
   PeerComm pc;
@@ -316,6 +332,7 @@ void ccg_destroy(ccg_ctx* ctx) {
   if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -1008,40 +1008,70 @@ int build_problem(ccg_ctx* ctx, const float* u, const float* v, const float* X, 
   CCG_CUDA(ctx, cudaMemcpyAsync(obs + 2 * n_obs, X + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(obs + 3 * n_obs, Y + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
   CCG_CUDA(ctx, cudaMemcpyAsync(obs + 4 * n_obs, Z + o0, sizeof(float) * n_obs, cudaMemcpyHostToDevice, st));
-  std::vector<int64_t> voff((size_t)n_views + 1);
-  for (int64_t i = 0; i <= n_views; ++i) voff[(size_t)i] = view_offsets[i] - o0;
+  // ---- per-view arrays: packed into the context's pinned staging arena (while the observation arrays above are on
+  // the wire) and uploaded behind them; pageable vectors only if the arena cannot be had
+  const size_t nv1 = (size_t)n_views + 1;
+  const size_t b_voff = sizeof(int64_t) * nv1, b_vmeta = sizeof(int2) * nv1, b_pose = sizeof(double) * (size_t)n_views * kPose,
+               b_items = sizeof(WorkItem) * items.size(), b_ranges = sizeof(int2) * ranges.size(),
+               b_intr = sizeof(double) * 9 * (size_t)n_problems, b_poff = sizeof(int64_t) * ((size_t)n_problems + 1);
+  auto up8 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t stage_bytes = up8(b_voff) + up8(b_vmeta) + up8(b_pose) + up8(b_items) + up8(b_ranges) + up8(b_intr) + up8(b_poff);
+  std::vector<unsigned char> pageable;
+  unsigned char* stage = static_cast<unsigned char*>(host_stage(ctx, stage_bytes));
+  if (!stage) {
+    pageable.resize(stage_bytes);
+    stage = pageable.data();
+  }
+  size_t cur = 0;
+  auto carve = [&](size_t bytes) {
+    unsigned char* q = stage + cur;
+    cur += up8(bytes);
+    return q;
+  };
+  int64_t* voff = reinterpret_cast<int64_t*>(carve(b_voff));
+  int2* vmeta = reinterpret_cast<int2*>(carve(b_vmeta));
+  double* pose = reinterpret_cast<double*>(carve(b_pose));
+  WorkItem* h_items = reinterpret_cast<WorkItem*>(carve(b_items));
+  int2* h_ranges = reinterpret_cast<int2*>(carve(b_ranges));
+  double* h_intr = reinterpret_cast<double*>(carve(b_intr));
+  int64_t* h_poff = reinterpret_cast<int64_t*>(carve(b_poff));
+  for (int64_t i = 0; i <= n_views; ++i) voff[i] = view_offsets[i] - o0;
   // block layout of the default sweep: every view padded to whole 32-observation blocks
-  std::vector<int2> vmeta((size_t)n_views + 1);
   int64_t n_blocks = 0;
   for (int64_t i = 0; i < n_views; ++i) {
     const int64_t n = view_offsets[i + 1] - view_offsets[i];
     if (n > 0x7fffffff || n_blocks > 0x7fffffff) return set_error(ctx, CCG_ERR_UNSUPPORTED, "view or problem too large");
-    vmeta[(size_t)i].x = (int)n_blocks;
-    vmeta[(size_t)i].y = (int)n;
+    vmeta[i].x = (int)n_blocks;
+    vmeta[i].y = (int)n;
     n_blocks += (n + 31) / 32;
   }
   if (n_blocks > 0x7fffffff) return set_error(ctx, CCG_ERR_UNSUPPORTED, "problem too large");
-  vmeta[(size_t)n_views].x = (int)n_blocks;
-  vmeta[(size_t)n_views].y = 0;
+  vmeta[n_views].x = (int)n_blocks;
+  vmeta[n_views].y = 0;
   int2* d_vmeta = nullptr;
   float* d_blk = nullptr;
-  CCG_TRY(dev_alloc(p, &d_vmeta, vmeta.size()));
+  CCG_TRY(dev_alloc(p, &d_vmeta, nv1));
   CCG_TRY(dev_alloc(p, &d_blk, (size_t)std::max<int64_t>(n_blocks, 1) * kObsBlock));
   d.vmeta = d_vmeta;
   d.obs_blk = d_blk;
-  CCG_CUDA(ctx, cudaMemcpyAsync(d_vmeta, vmeta.data(), sizeof(int2) * vmeta.size(), cudaMemcpyHostToDevice, st));
-  std::vector<double> pose((size_t)n_views * kPose, 0.0);
   for (int64_t i = 0; i < n_views; ++i) {
-    for (int k = 0; k < 4; ++k) pose[(size_t)i * kPose + k] = q[i * 4 + k];
-    for (int k = 0; k < 3; ++k) pose[(size_t)i * kPose + 4 + k] = t[i * 3 + k];
+    double* pp = pose + (size_t)i * kPose;
+    for (int k = 0; k < 4; ++k) pp[k] = q[i * 4 + k];
+    for (int k = 0; k < 3; ++k) pp[4 + k] = t[i * 3 + k];
+    for (int k = 7; k < kPose; ++k) pp[k] = 0.0;
   }
-  CCG_CUDA(ctx, cudaMemcpyAsync(d_voff, voff.data(), sizeof(int64_t) * voff.size(), cudaMemcpyHostToDevice, st));
-  CCG_CUDA(ctx, cudaMemcpyAsync(d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, st));
-  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_item_ranges, ranges.data(), sizeof(int2) * ranges.size(), cudaMemcpyHostToDevice, st));
-  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_pose0, pose.data(), sizeof(double) * pose.size(), cudaMemcpyHostToDevice, st));
-  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_intr0, intr, sizeof(double) * 9 * n_problems, cudaMemcpyHostToDevice, st));
+  std::memcpy(h_items, items.data(), b_items);
+  std::memcpy(h_ranges, ranges.data(), b_ranges);
+  std::memcpy(h_intr, intr, b_intr);
+  std::memcpy(h_poff, p->problem_off.data(), b_poff);
   CCG_TRY(dev_alloc(p, &p->d_problem_off, (size_t)n_problems + 1));
-  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_problem_off, p->problem_off.data(), sizeof(int64_t) * (n_problems + 1), cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(d_vmeta, vmeta, b_vmeta, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(d_voff, voff, b_voff, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(d_items, h_items, b_items, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_item_ranges, h_ranges, b_ranges, cudaMemcpyHostToDevice, st));
+  if (n_views > 0) CCG_CUDA(ctx, cudaMemcpyAsync(p->d_pose0, pose, b_pose, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_intr0, h_intr, b_intr, cudaMemcpyHostToDevice, st));
+  CCG_CUDA(ctx, cudaMemcpyAsync(p->d_problem_off, h_poff, b_poff, cudaMemcpyHostToDevice, st));
   if (n_views > 0) {
     k_intr_pack<<<(unsigned)((n_views * 32 + 255) / 256), 256, 0, st>>>(d, n_views, d_blk);
     ctx->launches++;
@@ -1556,6 +1586,54 @@ int ccg_intrinsics_estimate_batch(ccg_ctx* ctx, const float* u, const float* v, 
   };
   rc = body();
   free_problem(p);
+  return rc;
+}
+
+// EstimateHomography (reference src/geometry.cpp:70-107) for many point sets at once, on the device: the kernel the
+// initialisation of ccg_intrinsics_estimate runs, exposed so that it can be checked against the reference's own
+// known-answer test (src/test_geometry.cpp:172-194).
+int ccg_homography_batch(ccg_ctx* ctx, const float* x1, const float* y1, const float* x2, const float* y2,
+                         const int64_t* set_offsets, int64_t n_sets, double* H) {
+  if (!ctx || !set_offsets || n_sets < 0 || (n_sets > 0 && (!x1 || !y1 || !x2 || !y2 || !H))) return CCG_ERR_BAD_ARG;
+  if (n_sets == 0) return CCG_OK;
+  CCG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t o0 = set_offsets[0], n = set_offsets[n_sets] - o0;
+  for (int64_t i = 0; i < n_sets; ++i)
+    if (set_offsets[i + 1] < set_offsets[i]) return set_error(ctx, CCG_ERR_BAD_ARG, "set_offsets");
+  cudaStream_t st = ctx->stream;
+  float* d_pts = nullptr;
+  int64_t* d_off = nullptr;
+  double* d_H = nullptr;
+  auto body = [&]() -> int {
+    cudaError_t e = pool_alloc(ctx, (void**)&d_pts, sizeof(float) * 4 * std::max<int64_t>(n, 1));
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&d_off, sizeof(int64_t) * (n_sets + 1));
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&d_H, sizeof(double) * 9 * n_sets);
+    if (e != cudaSuccess) return set_error(ctx, CCG_ERR_CUDA, "device allocation", e);
+    std::vector<int64_t> off((size_t)n_sets + 1);
+    for (int64_t i = 0; i <= n_sets; ++i) off[(size_t)i] = set_offsets[i] - o0;
+    IntrDev d;
+    std::memset(&d, 0, sizeof(d));
+    d.X = d_pts;
+    d.Y = d_pts + n;
+    d.u = d_pts + 2 * n;
+    d.v = d_pts + 3 * n;
+    d.view_off = d_off;
+    CCG_CUDA(ctx, cudaMemcpyAsync(d_pts, x1 + o0, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CCG_CUDA(ctx, cudaMemcpyAsync(d_pts + n, y1 + o0, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CCG_CUDA(ctx, cudaMemcpyAsync(d_pts + 2 * n, x2 + o0, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CCG_CUDA(ctx, cudaMemcpyAsync(d_pts + 3 * n, y2 + o0, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CCG_CUDA(ctx, cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, st));
+    k_init_homography<<<(int)((n_sets + kInitWarps - 1) / kInitWarps), kInitWarps * 32, 0, st>>>(d, n_sets, d_H);
+    ctx->launches++;
+    CCG_CUDA(ctx, cudaMemcpyAsync(H, d_H, sizeof(double) * 9 * n_sets, cudaMemcpyDeviceToHost, st));
+    CCG_CUDA(ctx, cudaStreamSynchronize(st));
+    CCG_CUDA(ctx, cudaGetLastError());
+    return CCG_OK;
+  };
+  const int rc = body();
+  if (d_pts) pool_free(ctx, d_pts);
+  if (d_off) pool_free(ctx, d_off);
+  if (d_H) pool_free(ctx, d_H);
   return rc;
 }
 

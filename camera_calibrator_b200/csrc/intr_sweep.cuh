@@ -71,7 +71,13 @@ constexpr int kSwAheadJ = CCG_SW_AHEAD_J, kSwStagesJ = kSwAheadJ + 2;
 #ifndef CCG_SW_J2
 #define CCG_SW_J2 1
 #endif
-constexpr bool kSwD2 = CCG_SW_D2 != 0, kSwJ2 = CCG_SW_J2 != 0;
+#ifndef CCG_SW_DU2
+#define CCG_SW_DU2 1
+#endif
+#ifndef CCG_SW_JPIPE
+#define CCG_SW_JPIPE 1
+#endif
+constexpr bool kSwD2 = CCG_SW_D2 != 0, kSwJ2 = CCG_SW_J2 != 0, kSwDU2 = CCG_SW_DU2 != 0, kSwJPipe = CCG_SW_JPIPE != 0;
 // A Jacobian warp can also run the FP64 role on the last kSwTail / 64 of its pair's views once its own work is
 // done (static split: sums stay bit-reproducible).  Measured on C5: 0 .. 22 / 64 all within 2 % - the FP64 role is
 // bound by its pipe, not by the number of warps that feed it - so it is off by default.
@@ -79,7 +85,7 @@ constexpr bool kSwD2 = CCG_SW_D2 != 0, kSwJ2 = CCG_SW_J2 != 0;
 #define CCG_SW_TAIL 0
 #endif
 constexpr int kSwTail = CCG_SW_TAIL;
-constexpr int kSwTiles = kSwJ2 ? 2 : 1;  // Jacobian-row tiles per Jacobian warp
+constexpr int kSwTiles = (kSwJ2 || kSwJPipe) ? 2 : 1;  // Jacobian-row tiles per Jacobian warp
 constexpr int kObsBlock = 160;   // floats per 32-observation block in HBM: u v X Y Z
 constexpr int kSwStageD = 160;   // floats per stage: the whole block
 constexpr int kSwStageJ = 96;    // floats per stage: X Y Z
@@ -437,6 +443,15 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 #endif
 }
+// the same under a predicate instead of a branch (the request of a block stream sits in the hot loops: a branch
+// there costs a BSSY/BRA/BSYNC triple and a branch-resolving stall of the instruction that follows)
+__device__ __forceinline__ void cp_async16_if(bool on, unsigned dst, const void* src) {
+#ifdef CCG_SW_CG
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"((int)on) : "memory");
+#else
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"((int)on) : "memory");
+#endif
+}
 
 __device__ __forceinline__ void tc_store_rows(unsigned row_u, const float4 (&ur)[4], const float4 (&vr)[4]) {
   if (kSwF16) {
@@ -525,6 +540,7 @@ struct SwStream {
   unsigned ring, lane12;  // shared address of the ring; 12 * lane (piece offset - observation offset)
   unsigned fill, rd, rd_prev;  // this lane's piece of the stage to fill | its observation in the stage to read | read last
   __device__ __forceinline__ void request(int lane) {
+#ifdef CCG_SW_BRANCHY_REQUEST
     if (left > 0) {
       if (NARR == 5) {
         cp_async16(fill, src);
@@ -533,6 +549,14 @@ struct SwStream {
         if (lane < 24) cp_async16(fill, src);
       }
     }
+#else
+    if (NARR == 5) {
+      cp_async16_if(left > 0, fill, src);
+      cp_async16_if(left > 0 && lane < 8, fill + 512, src + 512);
+    } else {
+      cp_async16_if(left > 0 && lane < 24, fill, src);
+    }
+#endif
     asm volatile("cp.async.commit_group;" ::: "memory");
     src += kObsBlock * 4;
     --left;
@@ -672,7 +696,7 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, u
     int consumed = 0;  // blocks read so far, published for the partner's pacing
     auto load = [&]() -> SwObs5 {
       const unsigned a = strm.next(lane);
-      if (!LEAN) {
+      if (!LEAN && kSwLead > 0) {  // (published only when the partner is paced)
         ++consumed;
         if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(pace), "r"(consumed) : "memory");
       }
@@ -721,6 +745,17 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, u
           if (RES) res += 128;
         }
       }
+      if (kSwDU2 && !LEAN) {
+        // two chunks per trip, one after the other: the two-deep register queue (o0, o1) turns over in place, so the
+        // loop carries no register moves (the one-chunk loop below spends 10 of its 136 instructions on them)
+        for (; c >= 2; c -= 2) {
+          tc_fp64_observation<RES, false>(K, R, t, o0.mu, o0.mv, o0.X, o0.Y, o0.Z, true, gu, gv, cost, res);
+          o0 = load();
+          tc_fp64_observation<RES, false>(K, R, t, o1.mu, o1.mv, o1.X, o1.Y, o1.Z, true, gu, gv, cost, RES ? res + 64 : res);
+          o1 = load();
+          if (RES) res += 128;
+        }
+      }
       for (; c >= 1; --c) {
         const SwObs5 a = o0;
         o0 = o1;
@@ -752,7 +787,7 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, u
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
-  if (!LEAN && lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(pace), "r"(0x7fffffff) : "memory");
+  if (!LEAN && kSwLead > 0 && lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(pace), "r"(0x7fffffff) : "memory");
   // lane-private sums -> the warp's partial: [0] sum r^2 | [16..24] g_u
   double tmp[16];
 #pragma unroll
@@ -809,6 +844,21 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
     return o;
   };
   SwObs3 o0 = load(), o1 = load();
+  // destinations of this lane's eight product elements (view block slot, U slot; 0xff = none), packed four to a
+  // register once per work item: derived per view they cost more integer instructions than the epilogue itself
+  unsigned bsp[2] = {0u, 0u}, usp[2] = {0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int nt = i >> 2, e = i & 3;
+    const int row = g + ((e & 2) ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
+    bsp[i >> 2] |= (unsigned)(tc_blk_slot(row, col) & 0xff) << (8 * (i & 3));
+    usp[i >> 2] |= (unsigned)(tc_u_slot(row, col) & 0xff) << (8 * (i & 3));
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    bsp[i] = (unsigned)opaque((int)bsp[i]);
+    usp[i] = (unsigned)opaque((int)usp[i]);
+  }
   const unsigned row_u = tile + (unsigned)lane * (kTcRow * 4);            // this lane's u row (v row: + 32 rows)
   const unsigned frag = tile + (unsigned)(2 * tig * kTcRow + 2 * g) * 4;  // this lane's fragment of k-step 0
   float4 pn[3];
@@ -831,6 +881,41 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
     // per chunk: rows -> tile -> contraction.  The __syncwarp inside load() orders the previous chunk's tile
     // reads before this chunk's tile writes.
     int c = n >> 5;  // full chunks: no masking
+    if (kSwJPipe && c >= 2) {
+      // software pipeline inside the view: the rows of chunk j are computed while the tile of chunk j - 1 is
+      // contracted - the FP32 arithmetic has no dependence on the fragment loads and the HMMAs and is written
+      // BEFORE the tile store, so ptxas is free to fill the 8.6-cycle issue interval of the legacy tensor path
+      // with it.  Two tiles; the __syncwarp inside load() separates a tile's store from its fragment loads, and
+      // the fragment loads of one trip from the store into the same tile two trips later.
+      const unsigned t0 = 0u, t1 = kTcTile * 4;
+      float4 ur[4], vr[4];
+      tc_fp32_rows<false>(K, Rf, tf, o0.X, o0.Y, o0.Z, true, ur, vr);
+      tc_store_rows(row_u + t0, ur, vr);
+      o0 = load();  // queue now: o1 next, o0 after it
+      for (c -= 1; c >= 2; c -= 2) {
+        tc_fp32_rows<false>(K, Rf, tf, o1.X, o1.Y, o1.Z, true, ur, vr);
+        tc_contract<true>(frag + t0, 32, c0a, c0b, c1a, c1b);
+        tc_store_rows(row_u + t1, ur, vr);
+        o1 = load();
+        tc_fp32_rows<false>(K, Rf, tf, o0.X, o0.Y, o0.Z, true, ur, vr);
+        tc_contract<true>(frag + t1, 32, c0a, c0b, c1a, c1b);
+        tc_store_rows(row_u + t0, ur, vr);
+        o0 = load();
+      }
+      if (c == 1) {
+        tc_fp32_rows<false>(K, Rf, tf, o1.X, o1.Y, o1.Z, true, ur, vr);
+        tc_contract<true>(frag + t0, 32, c0a, c0b, c1a, c1b);
+        tc_store_rows(row_u + t1, ur, vr);
+        o1 = load();  // queue back in order: o0 next, o1 after it
+        tc_contract<true>(frag + t1, 32, c0a, c0b, c1a, c1b);
+      } else {
+        tc_contract<true>(frag + t0, 32, c0a, c0b, c1a, c1b);
+        const SwObs3 x = o0;
+        o0 = o1;
+        o1 = x;
+      }
+      c = 0;
+    }
     if (kSwJ2) {
       for (; c >= 2; c -= 2) {
         const SwObs3 a = o0, b = o1;
@@ -868,14 +953,14 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
     }
     // per-view epilogue: V, W blocks and the view's contribution to U
     double* blk = blk0 + (size_t)v * kBlk;
+    const double sc0 = tig < 3 ? isp * isp : isp;  // columns 0..7 of this lane: pose x pose (V) below column 6, else W
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int nt = i >> 2, e = i & 3;
-      const int row = g + ((e & 2) ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
       const float val = nt == 0 ? c0a[e] + c0b[e] : c1a[e] + c1b[e];
-      const int bs = tc_blk_slot(row, col), us = tc_u_slot(row, col);
-      if (bs >= 0) blk[bs] = (double)val * (col < 6 ? isp * isp : isp);  // V: pose x pose, W: pose x intrinsics
-      if (us >= 0) upart[us] += (double)val;  // one owner lane per slot within the warp
+      const unsigned bs = (bsp[i >> 2] >> (8 * (i & 3))) & 0xffu, us = (usp[i >> 2] >> (8 * (i & 3))) & 0xffu;
+      if (bs != 0xffu) blk[bs] = (double)val * (nt == 0 ? sc0 : isp);  // V: pose x pose, W: pose x intrinsics
+      if (us != 0xffu) upart[us] += (double)val;  // one owner lane per slot within the warp
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");

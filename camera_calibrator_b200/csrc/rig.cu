@@ -205,21 +205,52 @@ k_rig_sweep(RigDev d, double huber_a, double* __restrict__ res_out, double* __re
     double accf[21];  // warp A: V_f ; warp B: g_f in accf[0..5]
 #pragma unroll
     for (int i = 0; i < 21; ++i) accf[i] = 0.0;
+    // Loads run two steps ahead of the arithmetic (the world point is a gather through the point id, two dependent
+    // L2 round trips): step k computes on registers loaded during step k - 1 while the gather of step k + 1 and the
+    // point id of step k + 2 are in flight.  A segment's first two steps are primed before the reductions of the
+    // segment before it.  Out-of-range steps re-read the segment's last observation (never used).
+    int64_t o0 = d.seg_off[f * C], o1 = d.seg_off[f * C + 1];
+    int ip_a = 0, ip_b = 0;         // point ids of this lane's steps 0 and 1 of the segment
+    float mu_n = 0.f, mv_n = 0.f;   // measurement of step 0
+    auto prime_ids = [&](int64_t a0, int64_t a1) {
+      if (a0 < a1) {
+        const int64_t oa = min(a0 + lane, a1 - 1), ob = min(a0 + lane + 32, a1 - 1);
+        ip_a = __ldg(d.pt + oa);
+        ip_b = __ldg(d.pt + ob);
+        mu_n = __ldg(d.u + oa);
+        mv_n = __ldg(d.v + oa);
+      }
+    };
+    prime_ids(o0, o1);
     for (int c = 0; c < C; ++c) {
       double Rc[9], tc[3];
 #pragma unroll
       for (int i = 0; i < 9; ++i) Rc[i] = s_cam[c][i];
 #pragma unroll
       for (int i = 0; i < 3; ++i) tc[i] = s_cam[c][9 + i];
-      const int64_t o0 = d.seg_off[f * C + c], o1 = d.seg_off[f * C + c + 1];
+      const int64_t o2 = c + 1 < C ? d.seg_off[f * C + c + 2] : o1;  // end of the NEXT segment
       double acc[42];  // warp A: U_cc in acc[0..20] ; warp B: W_fc 36 | g_c 6
 #pragma unroll
       for (int i = 0; i < 42; ++i) acc[i] = 0.0;
+      float Xn = 0.f, Yn = 0.f, Zn = 0.f;
+      int ip_nn = ip_b;  // point id two steps ahead
+      if (o0 < o1) {
+        Xn = __ldg(d.Xw + 3 * (size_t)ip_a);
+        Yn = __ldg(d.Xw + 3 * (size_t)ip_a + 1);
+        Zn = __ldg(d.Xw + 3 * (size_t)ip_a + 2);
+      }
       for (int64_t o = o0 + lane; o < o1; o += 32) {
-        const int ip = __ldg(d.pt + o);
-        const float mu = __ldg(d.u + o), mv = __ldg(d.v + o);
-        const float Xf = __ldg(d.Xw + 3 * (size_t)ip), Yf = __ldg(d.Xw + 3 * (size_t)ip + 1),
-                    Zf = __ldg(d.Xw + 3 * (size_t)ip + 2);
+        const float mu = mu_n, mv = mv_n, Xf = Xn, Yf = Yn, Zf = Zn;
+        {
+          const int64_t on = min(o + 32, o1 - 1), onn = min(o + 64, o1 - 1);
+          const int ip1 = ip_nn;
+          ip_nn = __ldg(d.pt + onn);
+          mu_n = __ldg(d.u + on);
+          mv_n = __ldg(d.v + on);
+          Xn = __ldg(d.Xw + 3 * (size_t)ip1);
+          Yn = __ldg(d.Xw + 3 * (size_t)ip1 + 1);
+          Zn = __ldg(d.Xw + 3 * (size_t)ip1 + 2);
+        }
         RigGeom g;
         rig_geometry(Rf, tf, Rc, tc, (double)Xf, (double)Yf, (double)Zf, (double)mu, (double)mv, huber_a, g);
         if (cost_out) {
@@ -254,6 +285,10 @@ k_rig_sweep(RigDev d, double huber_a, double* __restrict__ res_out, double* __re
           }
         }
       }
+      // the next segment's first point ids and measurement, in flight during the reductions below
+      o0 = o1;
+      o1 = o2;
+      if (c + 1 < C) prime_ids(o0, o1);
       if (cost_out) continue;
       if (is_a) {
         double tmp[32];
@@ -425,62 +460,156 @@ __global__ void k_rig_schur(RigDev d, LmParams P) {
 }
 
 // fixed-order sum of the item partials: block b owns components [32b, 32b+32), thread
-// (c, seg) sums items seg, seg+8, ... and the 8 segment sums are combined in order
-__global__ void __launch_bounds__(256) k_rig_reduce(const double* __restrict__ part, int stride, int n_items,
-                                                    double* __restrict__ red) {
-  __shared__ double s_buf[8][32];
+// (c, seg) sums items seg, seg+32, ... (independent loads, all in flight at once) and the 32 segment
+// sums are combined in order
+constexpr int kRigRedSeg = 32;
+__global__ void __launch_bounds__(32 * kRigRedSeg) k_rig_reduce(const double* __restrict__ part, int stride, int n_items,
+                                                                double* __restrict__ red) {
+  __shared__ double s_buf[kRigRedSeg][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), seg = threadIdx.x >> 5;
   double s = 0.0;
-  if (c < stride)
-    for (int i = seg; i < n_items; i += 8) s += part[(size_t)i * stride + c];
+  if (c < stride) {
+#pragma unroll 8
+    for (int i = seg; i < n_items; i += kRigRedSeg) s += part[(size_t)i * stride + c];
+  }
   s_buf[seg][threadIdx.x & 31] = s;
   __syncthreads();
   if (seg == 0 && c < stride) {
     double tot = 0.0;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) tot += s_buf[g][threadIdx.x];
+    for (int g = 0; g < kRigRedSeg; ++g) tot += s_buf[g][threadIdx.x];
     red[c] = tot;
   }
 }
 
+// The LM state lives in global memory between launches; a single-CTA kernel stages it in shared memory, lets its
+// leader thread run the state machine there, and writes it back - a lone thread working on global memory pays an L2
+// round trip per dependent access (measured: 38 us per reduced solve of 18 unknowns, nearly all of it in those accesses).
+static_assert(sizeof(RigState) % sizeof(double) == 0, "RigState is staged as doubles");
+__device__ __forceinline__ void rig_state_in(RigState& sh, const RigState* g) {
+  for (int i = threadIdx.x; i < (int)(sizeof(RigState) / sizeof(double)); i += blockDim.x)
+    reinterpret_cast<double*>(&sh)[i] = reinterpret_cast<const double*>(g)[i];
+  __syncthreads();
+}
+__device__ __forceinline__ void rig_state_out(RigState* g, const RigState& sh) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < (int)(sizeof(RigState) / sizeof(double)); i += blockDim.x)
+    reinterpret_cast<double*>(g)[i] = reinterpret_cast<const double*>(&sh)[i];
+}
+
 __global__ void __launch_bounds__(256) k_rig_decide(RigDev d, LmParams P) {
   __shared__ double s_buf[kRigPart];
-  RigState& ps = d.ps[0];
-  if (ps.lm.status != 0) return;
+  __shared__ RigState ps;
+  if (d.ps[0].lm.status != 0) return;
+  rig_state_in(ps, d.ps);
   const bool evaluated = ps.lm.solve_ok != 0;
   if (evaluated) {
     for (int c = threadIdx.x; c < kRigPart; c += blockDim.x) s_buf[c] = d.red_sweep[c];
     __syncthreads();
   }
-  if (threadIdx.x != 0) return;
-  LmState& s = ps.lm;
-  if (!evaluated) {
-    lm_reject(s, P, d.n_done);
-    s.solve_ok = 1;
-    if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, d.n_done, true);
-    return;
-  }
-  const double* r = s_buf;
-  const int base = 27 * kMaxCams;
-  const bool accept = lm_decide(s, P, 0.5 * r[base], r[base + 2] + s.gTd_u, r[base + 3] + s.dDd_u, d.n_done);
-  if (accept) {
-    for (int c = 0; c < ps.n_cams; ++c) {
-      for (int e = 0; e < 21; ++e) ps.Ucc[c][e] = r[27 * c + e];
-      for (int e = 0; e < 6; ++e) ps.gc[c][e] = r[27 * c + 21 + e];
+  if (threadIdx.x == 0) {
+    LmState& s = ps.lm;
+    if (!evaluated) {
+      lm_reject(s, P, d.n_done);
+      s.solve_ok = 1;
+      if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, d.n_done, true);
+    } else {
+      const double* r = s_buf;
+      const int base = 27 * kMaxCams;
+      const bool accept = lm_decide(s, P, 0.5 * r[base], r[base + 2] + s.gTd_u, r[base + 3] + s.dDd_u, d.n_done);
+      if (accept) {
+        for (int c = 0; c < ps.n_cams; ++c) {
+          for (int e = 0; e < 21; ++e) ps.Ucc[c][e] = r[27 * c + e];
+          for (int e = 0; e < 6; ++e) ps.gc[c][e] = r[27 * c + 21 + e];
+        }
+        s.sumsq = r[base + 1];
+        s.n_obs = r[base + 4];
+      }
     }
-    s.sumsq = r[base + 1];
-    s.n_obs = r[base + 4];
   }
+  rig_state_out(d.ps, ps);
+}
+
+// the reduced step -> candidate camera extrinsics and the model terms g'd, d'Dd (one thread)
+__device__ __forceinline__ void rig_apply_step(RigState& ps, LmState& s, const double* x, const double* Du, int C, int par) {
+  double gTd = 0.0, dDd = 0.0;
+  for (int c = 0; c < C; ++c) {
+    double dc[6];
+    for (int i = 0; i < 6; ++i) {
+      dc[i] = ps.frozen[c] ? 0.0 : x[6 * c + i];
+      ps.du[6 * c + i] = dc[i];
+      gTd += ps.gc[c][i] * dc[i];
+      dDd += dc[i] * dc[i] * Du[6 * c + i];
+    }
+    double q[4] = {ps.cam[par][c][0], ps.cam[par][c][1], ps.cam[par][c][2], ps.cam[par][c][3]};
+    double qn[4];
+    quat_plus(q, dc[0], dc[1], dc[2], qn);
+    for (int i = 0; i < 4; ++i) ps.cam[par ^ 1][c][i] = qn[i];
+    for (int i = 0; i < 3; ++i) ps.cam[par ^ 1][c][4 + i] = ps.cam[par][c][4 + i] + dc[3 + i];
+  }
+  s.gTd_u = gTd;
+  s.dDd_u = dDd;
+  s.solve_ok = 1;
+}
+
+// S x = rhs for n <= N <= 32 by ONE warp: lane i holds row i of the lower triangle in registers (compile-time indices,
+// rows and columns beyond n padded with the identity), right-looking Cholesky with the pivot and the column broadcast
+// by shuffles, forward substitution on registers, back substitution on a transposed copy read back from shared
+// memory (a lane needs column i of L there).  The block-cooperative factorisation below pays three block barriers per
+// column and two per substituted unknown: 30 us at n = 24 against about 3 us here.  x is returned in rhs.
+template <int N>
+__device__ __forceinline__ bool rig_warp_solve(const double* S, double* rhs, double* T, int n, int i) {
+  const unsigned full = 0xffffffffu;
+  double row[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) row[k] = (i < n && k < n) ? S[i * n + k] : (k == i ? 1.0 : 0.0);
+  bool ok = true;
+  double inv_ii = 1.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double dd = __shfl_sync(full, row[j], j);
+    if (!(dd > 0.0) || !isfinite(dd)) ok = false;  // (uniform: dd is a broadcast)
+    const double inv = rsqrt(dd);
+    const double lij = row[j] * inv;  // lanes i > j: L[i][j]; lane j: L[j][j]
+    if (i == j) inv_ii = inv;
+    row[j] = lij;
+#pragma unroll
+    for (int k = j + 1; k < N; ++k) {
+      const double lkj = __shfl_sync(full, lij, k);
+      if (k <= i) row[k] = fma(-lij, lkj, row[k]);
+    }
+  }
+  if (!ok) return false;
+  const int ns = n | 1;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (i < n && k <= i) T[i * ns + k] = row[k];
+  __syncwarp();
+  double col[N];  // L[j][i], j > i
+#pragma unroll
+  for (int j = 0; j < N; ++j) col[j] = (j > i && j < n) ? T[j * ns + i] : 0.0;
+  double b = i < n ? rhs[i] : 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {  // L y = rhs
+    const double yj = __shfl_sync(full, b * inv_ii, j);
+    if (i == j) b = yj;
+    else if (i > j) b = fma(-row[j], yj, b);
+  }
+#pragma unroll
+  for (int j = N - 1; j >= 0; --j) {  // L' x = y
+    const double xj = __shfl_sync(full, b * inv_ii, j);
+    if (i == j) b = xj;
+    else if (i < j) b = fma(-col[j], xj, b);
+  }
+  if (i < n) rhs[i] = b;
+  __syncwarp();
+  return true;
 }
 
 // reduced (6C x 6C) solve, block-cooperative Cholesky and substitutions in (dynamic) shared memory:
 // S n x n | rhs n | Du n doubles, n = 6C <= 96
-__global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
-  extern __shared__ double s_dyn[];
-  __shared__ int s_flag[2];
-  __shared__ double s_piv;
-  RigState& ps = d.ps[0];
-  if (!(ps.lm.status == 0 || ps.lm.finalize)) return;
+__device__ __forceinline__ void rig_solve_body(const RigDev& d, const LmParams& P, RigState& ps, double* s_dyn, int* s_flag,
+                                               double& s_piv) {
   LmState& s = ps.lm;
   const int C = ps.n_cams, n = 6 * C, par = s.par, part = d.schur_stride;
   double* S = s_dyn;
@@ -548,6 +677,21 @@ __global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
   for (int a = threadIdx.x; a < n; a += blockDim.x)
     if (ps.frozen[a / 6]) rhs[a] = 0.0;
   __syncthreads();
+  if (n <= 32) {
+    // up to 5 cameras: ONE warp, lane i = row i, the factorisation in registers (see rig_warp_solve)
+    if (threadIdx.x >= 32) return;
+    double* T = Du + n;  // n x (n | 1) scratch behind S | rhs | Du: the transpose access of the back substitution
+    bool ok;
+    if (n <= 8) ok = rig_warp_solve<8>(S, rhs, T, n, threadIdx.x);
+    else if (n <= 16) ok = rig_warp_solve<16>(S, rhs, T, n, threadIdx.x);
+    else if (n <= 24) ok = rig_warp_solve<24>(S, rhs, T, n, threadIdx.x);
+    else ok = rig_warp_solve<32>(S, rhs, T, n, threadIdx.x);
+    if (threadIdx.x == 0) {
+      if (ok) rig_apply_step(ps, s, rhs, Du, C, par);
+      else s.solve_ok = 0;
+    }
+    return;
+  }
   // right-looking Cholesky, lower triangle, all threads
   for (int j = 0; j < n; ++j) {
     if (threadIdx.x == 0) {
@@ -593,24 +737,18 @@ __global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
     __syncthreads();
   }
   if (threadIdx.x != 0) return;
-  double gTd = 0.0, dDd = 0.0;
-  for (int c = 0; c < C; ++c) {
-    double dc[6];
-    for (int i = 0; i < 6; ++i) {
-      dc[i] = ps.frozen[c] ? 0.0 : rhs[6 * c + i];
-      ps.du[6 * c + i] = dc[i];
-      gTd += ps.gc[c][i] * dc[i];
-      dDd += dc[i] * dc[i] * Du[6 * c + i];
-    }
-    double q[4] = {ps.cam[par][c][0], ps.cam[par][c][1], ps.cam[par][c][2], ps.cam[par][c][3]};
-    double qn[4];
-    quat_plus(q, dc[0], dc[1], dc[2], qn);
-    for (int i = 0; i < 4; ++i) ps.cam[par ^ 1][c][i] = qn[i];
-    for (int i = 0; i < 3; ++i) ps.cam[par ^ 1][c][4 + i] = ps.cam[par][c][4 + i] + dc[3 + i];
-  }
-  s.gTd_u = gTd;
-  s.dDd_u = dDd;
-  s.solve_ok = 1;
+  rig_apply_step(ps, s, rhs, Du, C, par);
+}
+
+__global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
+  extern __shared__ double s_dyn[];
+  __shared__ int s_flag[2];
+  __shared__ double s_piv;
+  __shared__ RigState ps;
+  if (!(d.ps[0].lm.status == 0 || d.ps[0].lm.finalize)) return;
+  rig_state_in(ps, d.ps);
+  rig_solve_body(d, P, ps, s_dyn, s_flag, s_piv);  // (threads leave the body at different points; they meet again here)
+  rig_state_out(d.ps, ps);
 }
 
 __global__ void k_rig_init_state(RigDev d, LmParams P, const double* cam0, const int* frozen, int n_items,
@@ -813,7 +951,7 @@ int rig_build(ccg_ctx* ctx, const float* u, const float* v, const int32_t* obs_c
     p->schur_warps = 4;
     while (p->schur_warps > 1 && sizeof(double) * p->schur_warps * (part + cols) > 200 * 1024) p->schur_warps /= 2;
     p->schur_smem = sizeof(double) * p->schur_warps * (part + cols);
-    p->solve_smem = sizeof(double) * ((size_t)36 * C * C + 12 * C);
+    p->solve_smem = sizeof(double) * ((size_t)36 * C * C + 12 * C + (6 * C <= 32 ? (size_t)6 * C * ((6 * C) | 1) : 0));
     CCG_CUDA(ctx, cudaFuncSetAttribute(k_rig_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->schur_smem));
     CCG_CUDA(ctx, cudaFuncSetAttribute(k_rig_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->solve_smem));
   }
@@ -842,7 +980,7 @@ int rig_sweep_decide(ccg_rig_problem* p, const LmParams& P, Profiler& prof, doub
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
-  k_rig_reduce<<<(kRigPart + 31) / 32, 256, 0, st>>>(d.sweep_part, kRigPart, p->n_items, d.red_sweep);
+  k_rig_reduce<<<(kRigPart + 31) / 32, 32 * kRigRedSeg, 0, st>>>(d.sweep_part, kRigPart, p->n_items, d.red_sweep);
   if (p->shared && ctx->world > 1) {
     CCG_TRY(nccl_allreduce_sum(ctx, d.red_sweep, kRigPart));
     (*nar)++;
@@ -862,7 +1000,7 @@ int rig_schur_solve(ccg_rig_problem* p, const LmParams& P, Profiler& prof, int* 
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
-  k_rig_reduce<<<(d.schur_stride + 31) / 32, 256, 0, st>>>(d.schur_part, d.schur_stride, p->n_items, d.red_schur);
+  k_rig_reduce<<<(d.schur_stride + 31) / 32, 32 * kRigRedSeg, 0, st>>>(d.schur_part, d.schur_stride, p->n_items, d.red_schur);
   if (p->shared && ctx->world > 1) {
     CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, (size_t)d.schur_stride));
     (*nar)++;

@@ -54,8 +54,9 @@ typedef struct {
                                    sqrt(2 cost) is below the FP64 resolution of the cost: take it and stop */
   int32_t hessian_fp64;         /* single-camera sweep variant.  Residual, cost and gradient are FP64 in all of them (same
                                    fixed point); they differ in how the J'J blocks are formed:
-                                   0 (default) TF32 tensor-core products of float32 Jacobian rows, 1 everything in
-                                   FP64 */
+                                   0 (default) tensor-core products (mma.sync m16n8k16, FP32 accumulation) of the
+                                   float32 Jacobian rows rounded to FP16 (11 significant bits, as TF32; pose columns
+                                   scaled by a power of two into range), 1 everything in FP64 */
   int32_t reserved_;
 } ccg_opts;
 
@@ -148,6 +149,13 @@ int ccg_intrinsics_estimate_batch(ccg_ctx* ctx, const float* u, const float* v, 
                                   int64_t n_problems, double* intr, double* q, double* t,
                                   double* intr_init, uint32_t const_intr_mask, const ccg_opts* opts,
                                   ccg_report* reports);
+
+/* EstimateHomography (reference src/geometry.cpp:70-107) for n_sets point sets at once: set i maps the points
+ * (x1, y1)[set_offsets[i] .. set_offsets[i+1]) to (x2, y2) of the same range.  H receives 9 doubles per set (row-major,
+ * unit Frobenius norm; the caller divides by H[8] as the reference's users do); H[9 i] is NaN for a set with fewer than
+ * 4 points or degenerate geometry.  This is the first kernel of ccg_intrinsics_estimate's initialisation. */
+int ccg_homography_batch(ccg_ctx* ctx, const float* x1, const float* y1, const float* x2, const float* y2,
+                         const int64_t* set_offsets, int64_t n_sets, double* H);
 
 /* Batched lens model of calibrator::Calibrator, host buffers in and out.
  * ccg_undistort: pixels -> undistorted normalised coordinates (Calibrator::Undistort, reference

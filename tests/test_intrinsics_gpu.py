@@ -189,6 +189,37 @@ def test_estimate_device_init_then_solve(ctx, nv, npts, seed):
             assert breps[b]["termination"] in (1, 2, 3)
 
 
+def test_device_homography_known_answer(ctx):
+    """The reference's own known-answer test for EstimateHomography (src/test_geometry.cpp:172-194: a random H with
+    H(2,2) = 1 is recovered from 10 exact correspondences to 1e-4), run on the DEVICE kernel of the initialisation
+    (k_init_homography behind ccg_homography_batch), 200 point sets in one call, against the oracle's SVD as well."""
+    rng = np.random.default_rng(0)
+    n_sets, n_pts = 200, 10
+    Hs = rng.uniform(-1, 1, (n_sets, 3, 3)).astype(np.float32)
+    Hs /= Hs[:, 2:3, 2:3]
+    p1 = np.concatenate([rng.uniform(-1, 1, (n_sets, n_pts, 2)), np.ones((n_sets, n_pts, 1))], 2).astype(np.float32)
+    p2 = np.einsum("sij,spj->spi", Hs.astype(np.float64), p1.astype(np.float64))
+    keep = np.min(np.abs(p2[:, :, 2]), axis=1) > 0.2   # (sets whose points stay away from the line at infinity)
+    p2 = (p2 / p2[:, :, 2:]).astype(np.float32)
+    off = np.arange(n_sets + 1, dtype=np.int64) * n_pts
+    got = ctx.homography_batch(p1[:, :, 0].ravel(), p1[:, :, 1].ravel(), p2[:, :, 0].ravel(), p2[:, :, 1].ravel(), off)
+    assert keep.sum() >= 50
+    for s in np.nonzero(keep)[0]:
+        H2 = got[s] / got[s, 2, 2]
+        assert np.max(np.abs(Hs[s] - H2)) <= 1e-4, s
+        Ho = oracle.homography(p1[s, :, 0], p1[s, :, 1], p2[s, :, 0], p2[s, :, 1])
+        assert np.max(np.abs(Ho / Ho[2, 2] - H2)) <= 1e-4
+    # ragged and degenerate sets: 3 points -> NaN marker, the others unaffected
+    off2 = np.array([0, 3, 13, 23], dtype=np.int64)
+    x1 = np.concatenate([p1[0, :3, 0], p1[1, :, 0], p1[2, :, 0]])
+    y1 = np.concatenate([p1[0, :3, 1], p1[1, :, 1], p1[2, :, 1]])
+    x2 = np.concatenate([p2[0, :3, 0], p2[1, :, 0], p2[2, :, 0]])
+    y2 = np.concatenate([p2[0, :3, 1], p2[1, :, 1], p2[2, :, 1]])
+    g2 = ctx.homography_batch(x1, y1, x2, y2, off2)
+    assert np.isnan(g2[0, 0, 0])
+    assert np.array_equal(g2[1], got[1]) and np.array_equal(g2[2], got[2])
+
+
 def test_estimate_needs_three_views(ctx):
     import camera_calibrator_b200 as cc
 
