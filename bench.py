@@ -490,6 +490,7 @@ def run_ours(args):
     n_prof = 2
     sweep_ms = schur_ms = small_ms = 0.0
     n_sweeps = 0
+    prob.run(opts_prof)  # untimed: small problems ran the persistent kernel so far, the multi-launch kernels load here
     for _ in range(n_prof):
         tm = prob.run(opts_prof)
         sweep_ms += tm["sweep_ms"]

@@ -239,23 +239,13 @@ k_rig_sweep(RigDev d, double huber_a, double* __restrict__ res_out, double* __re
         Yn = __ldg(d.Xw + 3 * (size_t)ip_a + 1);
         Zn = __ldg(d.Xw + 3 * (size_t)ip_a + 2);
       }
-      for (int64_t o = o0 + lane; o < o1; o += 32) {
-        const float mu = mu_n, mv = mv_n, Xf = Xn, Yf = Yn, Zf = Zn;
-        {
-          const int64_t on = min(o + 32, o1 - 1), onn = min(o + 64, o1 - 1);
-          const int ip1 = ip_nn;
-          ip_nn = __ldg(d.pt + onn);
-          mu_n = __ldg(d.u + on);
-          mv_n = __ldg(d.v + on);
-          Xn = __ldg(d.Xw + 3 * (size_t)ip1);
-          Yn = __ldg(d.Xw + 3 * (size_t)ip1 + 1);
-          Zn = __ldg(d.Xw + 3 * (size_t)ip1 + 2);
-        }
+      // one step: the observation at o from registers
+      auto step = [&](int64_t o, float mu, float mv, float Xf, float Yf, float Zf) {
         RigGeom g;
         rig_geometry(Rf, tf, Rc, tc, (double)Xf, (double)Yf, (double)Zf, (double)mu, (double)mv, huber_a, g);
         if (cost_out) {
           if (is_a) cost_out[o] = 0.5 * g.rho;
-          continue;
+          return;
         }
         if (is_a) {
           if (res_out) {
@@ -283,6 +273,33 @@ k_rig_sweep(RigDev d, double huber_a, double* __restrict__ res_out, double* __re
             accf[a] = fma(g.jfu[a], g.ru, fma(g.jfv[a], g.rv, accf[a]));
             acc[36 + a] = fma(g.jcu[a], g.ru, fma(g.jcv[a], g.rv, acc[36 + a]));
           }
+        }
+      };
+      // the loads of step k + 1 (gather through the id fetched a step earlier) and the id of step k + 2
+      auto fetch = [&](int64_t o, int& ip_next, float& mu, float& mv, float& Xf, float& Yf, float& Zf) {
+        const int64_t on = min(o + 32, o1 - 1), onn = min(o + 64, o1 - 1);
+        const int ip1 = ip_next;
+        ip_next = __ldg(d.pt + onn);
+        mu = __ldg(d.u + on);
+        mv = __ldg(d.v + on);
+        Xf = __ldg(d.Xw + 3 * (size_t)ip1);
+        Yf = __ldg(d.Xw + 3 * (size_t)ip1 + 1);
+        Zf = __ldg(d.Xw + 3 * (size_t)ip1 + 2);
+      };
+      // two steps per trip on two register sets (A: mu_n .. Zn, B): the sets swap roles instead of being copied -
+      // with a copy, ptxas moved the "next" registers into the "current" ones at the TOP of the step and so waited
+      // for the loads it had just issued (14 % of all stall samples on that one move)
+      {
+        float mu_b = 0.f, mv_b = 0.f, Xb = 0.f, Yb = 0.f, Zb = 0.f;
+        int64_t o = o0 + lane;
+        while (o < o1) {
+          fetch(o, ip_nn, mu_b, mv_b, Xb, Yb, Zb);
+          step(o, mu_n, mv_n, Xn, Yn, Zn);
+          o += 32;
+          if (!(o < o1)) break;
+          fetch(o, ip_nn, mu_n, mv_n, Xn, Yn, Zn);
+          step(o, mu_b, mv_b, Xb, Yb, Zb);
+          o += 32;
         }
       }
       // the next segment's first point ids and measurement, in flight during the reductions below
@@ -497,13 +514,40 @@ __device__ __forceinline__ void rig_state_out(RigState* g, const RigState& sh) {
     reinterpret_cast<double*>(g)[i] = reinterpret_cast<const double*>(&sh)[i];
 }
 
-__global__ void __launch_bounds__(256) k_rig_decide(RigDev d, LmParams P) {
+// FUSED: the kernel also reduces the per-item sweep partials itself (one launch instead of k_rig_reduce + k_rig_decide;
+// a problem that is not partitioned over GPUs needs nothing in between).  1024 threads: thread (c, seg) sums items
+// seg, seg + 8, ... of component c, the 8 segment sums are combined in order - only the 27 C + 5 components in use.
+template <bool FUSED>
+__global__ void __launch_bounds__(FUSED ? 1024 : 256) k_rig_decide(RigDev d, LmParams P, int n_items) {
   __shared__ double s_buf[kRigPart];
+  __shared__ double s_seg[8][128];
   __shared__ RigState ps;
   if (d.ps[0].lm.status != 0) return;
   rig_state_in(ps, d.ps);
   const bool evaluated = ps.lm.solve_ok != 0;
-  if (evaluated) {
+  if (evaluated && FUSED) {
+    const int C = d.n_cams, ncomp = 27 * C + 5;
+    for (int c = threadIdx.x; c < kRigPart; c += blockDim.x) s_buf[c] = 0.0;
+    const int lc = threadIdx.x & 127, seg = threadIdx.x >> 7;
+    for (int c0 = 0; c0 < ncomp; c0 += 128) {
+      const int idx = c0 + lc;
+      const int comp = idx < 27 * C ? idx : 27 * kMaxCams + (idx - 27 * C);
+      double sum = 0.0;
+      if (idx < ncomp) {
+#pragma unroll 8
+        for (int i = seg; i < n_items; i += 8) sum += d.sweep_part[(size_t)i * kRigPart + comp];
+      }
+      s_seg[seg][lc] = sum;
+      __syncthreads();
+      if (seg == 0 && idx < ncomp) {
+        double tot = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) tot += s_seg[g][lc];
+        s_buf[comp] = tot;
+      }
+      __syncthreads();
+    }
+  } else if (evaluated) {
     for (int c = threadIdx.x; c < kRigPart; c += blockDim.x) s_buf[c] = d.red_sweep[c];
     __syncthreads();
   }
@@ -552,56 +596,57 @@ __device__ __forceinline__ void rig_apply_step(RigState& ps, LmState& s, const d
   s.solve_ok = 1;
 }
 
-// S x = rhs for n <= N <= 32 by ONE warp: lane i holds row i of the lower triangle in registers (compile-time indices,
-// rows and columns beyond n padded with the identity), right-looking Cholesky with the pivot and the column broadcast
-// by shuffles, forward substitution on registers, back substitution on a transposed copy read back from shared
-// memory (a lane needs column i of L there).  The block-cooperative factorisation below pays three block barriers per
-// column and two per substituted unknown: 30 us at n = 24 against about 3 us here.  x is returned in rhs.
-template <int N>
-__device__ __forceinline__ bool rig_warp_solve(const double* S, double* rhs, double* T, int n, int i) {
+// S x = rhs for n <= 32 by ONE warp, warp barriers only.  Right-looking Cholesky on a copy T of S (row stride n | 1:
+// a column is conflict-free): lane k owns COLUMN k of the trailing matrix and updates its rows k .. n-1 in batches of
+// four (loads of a batch in flight together); then the substitutions with unknown i in a register of lane i and the
+// pivots broadcast by shuffles.  Compact loops on purpose: a fully unrolled register-resident version (tried) is
+// 250 KB of straight-line code and runs at instruction-fetch speed.  The block-cooperative factorisation below pays
+// three block barriers per column and two per substituted unknown: 30 us at n = 24.  x is returned in rhs.
+__device__ __forceinline__ bool rig_warp_solve(const double* S, double* rhs, double* T, int n, int lane) {
   const unsigned full = 0xffffffffu;
-  double row[N];
-#pragma unroll
-  for (int k = 0; k < N; ++k) row[k] = (i < n && k < n) ? S[i * n + k] : (k == i ? 1.0 : 0.0);
-  bool ok = true;
-  double inv_ii = 1.0;
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const double dd = __shfl_sync(full, row[j], j);
-    if (!(dd > 0.0) || !isfinite(dd)) ok = false;  // (uniform: dd is a broadcast)
-    const double inv = rsqrt(dd);
-    const double lij = row[j] * inv;  // lanes i > j: L[i][j]; lane j: L[j][j]
-    if (i == j) inv_ii = inv;
-    row[j] = lij;
-#pragma unroll
-    for (int k = j + 1; k < N; ++k) {
-      const double lkj = __shfl_sync(full, lij, k);
-      if (k <= i) row[k] = fma(-lij, lkj, row[k]);
-    }
-  }
-  if (!ok) return false;
   const int ns = n | 1;
-#pragma unroll
-  for (int k = 0; k < N; ++k)
-    if (i < n && k <= i) T[i * ns + k] = row[k];
+  if (lane < n)
+    for (int k = 0; k < n; ++k) T[lane * ns + k] = S[lane * n + k];
   __syncwarp();
-  double col[N];  // L[j][i], j > i
-#pragma unroll
-  for (int j = 0; j < N; ++j) col[j] = (j > i && j < n) ? T[j * ns + i] : 0.0;
-  double b = i < n ? rhs[i] : 0.0;
-#pragma unroll
-  for (int j = 0; j < N; ++j) {  // L y = rhs
-    const double yj = __shfl_sync(full, b * inv_ii, j);
-    if (i == j) b = yj;
-    else if (i > j) b = fma(-row[j], yj, b);
+  double inv_ll = 1.0;  // 1 / L[lane][lane]
+  for (int j = 0; j < n; ++j) {
+    const double dd = T[j * ns + j];
+    if (!(dd > 0.0) || !isfinite(dd)) return false;  // (uniform)
+    const double inv = rsqrt(dd);
+    if (lane == j) inv_ll = inv;
+    __syncwarp();
+    if (lane > j && lane < n) T[lane * ns + j] *= inv;
+    __syncwarp();
+    if (lane > j && lane < n) {
+      const double lkj = T[lane * ns + j];
+      int i = lane;
+      for (; i + 3 < n; i += 4) {
+        const double a0 = T[i * ns + j], a1 = T[(i + 1) * ns + j], a2 = T[(i + 2) * ns + j], a3 = T[(i + 3) * ns + j];
+        const double c0 = T[i * ns + lane], c1 = T[(i + 1) * ns + lane], c2 = T[(i + 2) * ns + lane],
+                     c3 = T[(i + 3) * ns + lane];
+        T[i * ns + lane] = fma(-a0, lkj, c0);
+        T[(i + 1) * ns + lane] = fma(-a1, lkj, c1);
+        T[(i + 2) * ns + lane] = fma(-a2, lkj, c2);
+        T[(i + 3) * ns + lane] = fma(-a3, lkj, c3);
+      }
+      for (; i < n; ++i) T[i * ns + lane] = fma(-T[i * ns + j], lkj, T[i * ns + lane]);
+    }
+    __syncwarp();
   }
-#pragma unroll
-  for (int j = N - 1; j >= 0; --j) {  // L' x = y
-    const double xj = __shfl_sync(full, b * inv_ii, j);
-    if (i == j) b = xj;
-    else if (i < j) b = fma(-col[j], xj, b);
+  double b = lane < n ? rhs[lane] : 0.0;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {  // L y = rhs
+    const double lij = (lane > j && lane < n) ? T[lane * ns + j] : 0.0;
+    const double yj = __shfl_sync(full, b * inv_ll, j);
+    b = lane == j ? yj : fma(-lij, yj, b);
   }
-  if (i < n) rhs[i] = b;
+#pragma unroll 4
+  for (int j = n - 1; j >= 0; --j) {  // L' x = y
+    const double lji = lane < j ? T[j * ns + lane] : 0.0;
+    const double xj = __shfl_sync(full, b * inv_ll, j);
+    b = lane == j ? xj : fma(-lji, xj, b);
+  }
+  if (lane < n) rhs[lane] = b;
   __syncwarp();
   return true;
 }
@@ -678,14 +723,10 @@ __device__ __forceinline__ void rig_solve_body(const RigDev& d, const LmParams& 
     if (ps.frozen[a / 6]) rhs[a] = 0.0;
   __syncthreads();
   if (n <= 32) {
-    // up to 5 cameras: ONE warp, lane i = row i, the factorisation in registers (see rig_warp_solve)
+    // up to 5 cameras: ONE warp (see rig_warp_solve)
     if (threadIdx.x >= 32) return;
     double* T = Du + n;  // n x (n | 1) scratch behind S | rhs | Du: the transpose access of the back substitution
-    bool ok;
-    if (n <= 8) ok = rig_warp_solve<8>(S, rhs, T, n, threadIdx.x);
-    else if (n <= 16) ok = rig_warp_solve<16>(S, rhs, T, n, threadIdx.x);
-    else if (n <= 24) ok = rig_warp_solve<24>(S, rhs, T, n, threadIdx.x);
-    else ok = rig_warp_solve<32>(S, rhs, T, n, threadIdx.x);
+    const bool ok = rig_warp_solve(S, rhs, T, n, threadIdx.x);
     if (threadIdx.x == 0) {
       if (ok) rig_apply_step(ps, s, rhs, Du, C, par);
       else s.solve_ok = 0;
@@ -980,13 +1021,16 @@ int rig_sweep_decide(ccg_rig_problem* p, const LmParams& P, Profiler& prof, doub
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
-  k_rig_reduce<<<(kRigPart + 31) / 32, 32 * kRigRedSeg, 0, st>>>(d.sweep_part, kRigPart, p->n_items, d.red_sweep);
   if (p->shared && ctx->world > 1) {
+    k_rig_reduce<<<(kRigPart + 31) / 32, 32 * kRigRedSeg, 0, st>>>(d.sweep_part, kRigPart, p->n_items, d.red_sweep);
     CCG_TRY(nccl_allreduce_sum(ctx, d.red_sweep, kRigPart));
     (*nar)++;
+    k_rig_decide<false><<<1, 256, 0, st>>>(d, P, p->n_items);
+    ctx->launches += 2;
+  } else {
+    k_rig_decide<true><<<1, 1024, 0, st>>>(d, P, p->n_items);
+    ctx->launches++;
   }
-  k_rig_decide<<<1, 256, 0, st>>>(d, P);
-  ctx->launches += 2;
   prof.end();
   return CCG_OK;
 }

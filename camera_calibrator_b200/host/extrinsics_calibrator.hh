@@ -12,6 +12,8 @@
 
 namespace calibrator {
 
+// Limit of this build: at most 16 cameras (AddCameraTRig accepts more, Optimize then throws with
+// CCG_ERR_UNSUPPORTED; the reference has no bound, extrinsics_calibrator.cpp:9-17).
 class ExtrinsicsCalibrator {
  public:
   /// \return Camera ID

@@ -32,3 +32,18 @@ for name, arrs in (("pageable", (d.u, d.v, d.X, d.Y, d.Z)), ("pinned", (hu, hv, 
     t0 = time.perf_counter()
     r = ctx.intrinsics_solve(*arrs, d.view_offsets, intr, q, t)
     print(f"{name} one-call solve: {1e3*(time.perf_counter()-t0):.1f} ms")
+
+# the PCIe floor of this box: one 800 MB pinned host -> device copy, and the same as five 160 MB copies
+x = torch.empty(200_000_000, dtype=torch.float32).pin_memory()
+y = torch.empty(200_000_000, dtype=torch.float32, device="cuda")
+for rep in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    y.copy_(x, non_blocking=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for i in range(5):
+        y[i * 40_000_000:(i + 1) * 40_000_000].copy_(x[i * 40_000_000:(i + 1) * 40_000_000], non_blocking=True)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"H2D 800 MB pinned: {1e3*(t1-t0):.2f} ms ({0.8/(t1-t0):.1f} GB/s); as 5 copies: {1e3*(t2-t1):.2f} ms")
