@@ -675,9 +675,11 @@ struct SwObs3 {
 };
 
 // LEAN (the Jacobian warps' share, fewer registers): one chunk at a time, the pose is loaded at the view's start.
+// strm: the warp's block stream over [va, vb), already initialised (its first blocks are in flight: sw_sweep_item
+// starts the streams BEFORE the candidate poses are computed, so the first HBM round trip hides behind that phase).
 template <bool RES, bool LEAN>
-__device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, unsigned pace, const double* s_k, int par,
-                                            int va, int vb, int lane, double* upart, double* __restrict__ res_out) {
+__device__ __forceinline__ void sw_run_fp64(const IntrDev& d, SwStream<5, kSwAheadD>& strm, unsigned pace, const double* s_k,
+                                            int par, int va, int vb, int lane, double* upart, double* __restrict__ res_out) {
   TcConst64 K;
   K.fx = s_k[0]; K.fy = s_k[1]; K.cx = s_k[2]; K.cy = s_k[3];
   K.k1 = s_k[4]; K.k2 = s_k[5]; K.p1 = s_k[6]; K.p2 = s_k[7]; K.k3 = s_k[8];
@@ -689,8 +691,6 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, u
     const int2* vmeta = opaque_ptr(d.vmeta);
     const double2* rt = reinterpret_cast<const double2*>(opaque_ptr(d.rt));
     double* gv_out = opaque_ptr(d.blk[par ^ 1] + 21 + lane);
-    SwStream<5, kSwAheadD> strm;
-    strm.init(d.obs_blk, vmeta[va].x, vmeta[vb].x, (unsigned)opaque((int)stages), lane);
     // the lane keeps the observations of the next two chunks of its stream in registers (o0: next, o1: the one
     // after): the shared-memory latency of a chunk hides behind the arithmetic of the chunks before it
     int consumed = 0;  // blocks read so far, published for the partner's pacing
@@ -805,9 +805,12 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, unsigned stages, u
 // The Jacobian + tensor role over the views [va, vb): V, W (into the view blocks) and U (into the
 // warp's partial).  `stages`, `tile` = shared addresses.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, unsigned tile, unsigned pace, const double* s_k,
-                                           int par, int va, int vb, int lane, double* upart) {
-  if (va >= vb) return;
+__device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAheadJ>& strm, unsigned tile, unsigned pace,
+                                           const double* s_k, int par, int va, int vb, int lane, double* upart) {
+  if (va >= vb) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return;
+  }
   lane = opaque(lane);
   tile = (unsigned)opaque((int)tile);
   const int g = lane >> 2, tig = lane & 3;
@@ -822,8 +825,6 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, unsigned stages, un
   const int2* vmeta = opaque_ptr(d.vmeta);
   const float4* rtf = reinterpret_cast<const float4*>(opaque_ptr(d.rtf));
   double* blk0 = opaque_ptr(d.blk[par ^ 1]);
-  SwStream<3, kSwAheadJ> strm;
-  strm.init(d.obs_blk, vmeta[va].x, vmeta[vb].x, (unsigned)opaque((int)stages), lane);
   int requested = 0;
   auto load = [&]() -> SwObs3 {
     // pacing: stay within kSwLead blocks of the FP64 partner (see kSwLead)
@@ -994,33 +995,58 @@ __device__ __forceinline__ void sw_sweep_item(const IntrDev& d, const WorkItem& 
                                               double* s_step, double* out, double* __restrict__ res_out) {
   for (int i = threadIdx.x; i < kSwWarps * kSweepPart; i += kSwThreads) (&sm.part[0][0])[i] = 0.0;
   if (threadIdx.x < kSwPairs) sm.pace[threadIdx.x] = 0;
-  sw_candidate_poses(d, it, par, s_du, s_red, s_step);  // (its barrier also covers the zeroing above)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* upart = sm.part[warp];
   // pair p (Jacobian warp p, FP64 warp kSwPairs + p, same SM sub-partition) owns the p-th part of the item's views
   const int pair = warp & (kSwPairs - 1), nv = it.v1 - it.v0;
   const int va = it.v0 + (int)((int64_t)nv * pair / kSwPairs), vb = it.v0 + (int)((int64_t)nv * (pair + 1) / kSwPairs);
   const int vsplit = va + ((vb - va) * (64 - kSwTail) + 32) / 64;  // FP64 role: [va, vsplit) the FP64 warp, the rest its partner
-  if (ROLE == 1 || (ROLE == 0 && warp >= kSwPairs)) {
+  const bool is_d = ROLE == 1 || (ROLE == 0 && warp >= kSwPairs);
+  // The block streams start here: they depend on the observations only, so their first requests are on the way to HBM
+  // while the candidate poses are computed (per CTA a microsecond or two - 8 % of the sweep of a 50-view problem).
+  // (Measured: -2.5 % per launch on C4's 50-view problems, nothing at C5; the persistent LM kernel, ROLE 1 / 2, starts
+  // its streams after the poses - there the early start measured slightly slower.)
+  SwStream<5, kSwAheadD> strm_d;
+  SwStream<3, kSwAheadJ> strm_j;
+#ifndef CCG_SW_LATE_STREAMS
+  constexpr bool kEarly = ROLE == 0;
+#else
+  constexpr bool kEarly = false;
+#endif
+  if (kEarly) {
+    if (is_d) strm_d.init(d.obs_blk, d.vmeta[va].x, d.vmeta[vsplit].x, smem_u32(sm.stage_d + pair * kSwStagesD * kSwStageD), lane);
+    else strm_j.init(d.obs_blk, d.vmeta[va].x, d.vmeta[vb].x, smem_u32(sm.stage_j + pair * kSwStagesJ * kSwStageJ), lane);
+  }
+  sw_candidate_poses(d, it, par, s_du, s_red, s_step);  // (its barrier also covers the zeroing above)
+  if (!kEarly) {
+    if (is_d) strm_d.init(d.obs_blk, d.vmeta[va].x, d.vmeta[vsplit].x, smem_u32(sm.stage_d + pair * kSwStagesD * kSwStageD), lane);
+    else strm_j.init(d.obs_blk, d.vmeta[va].x, d.vmeta[vb].x, smem_u32(sm.stage_j + pair * kSwStagesJ * kSwStageJ), lane);
+  }
+  if (is_d) {
     // =========================== FP64 role ===========================
     if (ROLE == 0 && kSwRegD > kSwRegLaunch) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSwRegD));
 #ifndef CCG_SW_ONLY_J  // timing experiments: one role alone (results are then incomplete)
-    sw_run_fp64<RES, false>(d, smem_u32(sm.stage_d + pair * kSwStagesD * kSwStageD), smem_u32(sm.pace + pair), s_k, par, va,
-                            vsplit, lane, upart, res_out);
+    sw_run_fp64<RES, false>(d, strm_d, smem_u32(sm.pace + pair), s_k, par, va, vsplit, lane, upart, res_out);
+#else
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
   } else {
     // =========================== Jacobian + tensor role ===========================
     if (ROLE == 0 && kSwRegJ < kSwRegLaunch) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSwRegJ));
 #ifndef CCG_SW_ONLY_D
-    sw_run_jac(d, smem_u32(sm.stage_j + pair * kSwStagesJ * kSwStageJ), smem_u32(sm.tiles + pair * kSwTiles * kTcTile),
-               smem_u32(sm.pace + pair), s_k, par, va, vb, lane, upart);
+    sw_run_jac(d, strm_j, smem_u32(sm.tiles + pair * kSwTiles * kTcTile), smem_u32(sm.pace + pair), s_k, par, va, vb, lane,
+               upart);
+#else
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 #if !defined(CCG_SW_ONLY_J) || defined(CCG_SW_TAIL_ANYWAY)
     // the tail of the pair's FP64 work; the ring lives in the tile(s), free by now (every lane is past its last
-    // tile read: sw_run_fp64 synchronises the warp before the first ring write lands)
+    // tile read: the warp is synchronised before the first ring write lands)
     if (kSwTail > 0) {
       __syncwarp();
-      sw_run_fp64<RES, true>(d, smem_u32(sm.tiles + pair * kSwTiles * kTcTile), 0u, s_k, par, vsplit, vb, lane, upart, res_out);
+      SwStream<5, kSwAheadD> strm_t;
+      strm_t.init(d.obs_blk, d.vmeta[vsplit].x, d.vmeta[vb].x, smem_u32(sm.tiles + pair * kSwTiles * kTcTile), lane);
+      sw_run_fp64<RES, true>(d, strm_t, 0u, s_k, par, vsplit, vb, lane, upart, res_out);
     }
 #endif
   }
