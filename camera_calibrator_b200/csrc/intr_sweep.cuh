@@ -62,9 +62,9 @@ static_assert(kSwRegD >= kSwRegLaunch && kSwRegD <= 256 && kSwRegJ % 8 == 0, "re
 #endif
 constexpr int kSwAheadD = CCG_SW_AHEAD_D, kSwStagesD = kSwAheadD + 2;  // blocks in flight / ring size
 constexpr int kSwAheadJ = CCG_SW_AHEAD_J, kSwStagesJ = kSwAheadJ + 2;
-// chunks a warp works on at a time (2 = two chunks per loop trip).  Measured on C5: no effect for either role -
-// ptxas serialises the two chains under the register budget, and the kernel is bound by the pipe FP64 and
-// legacy tensor instructions share, not by dependent-issue latency (profiles/r02_sweep_experiments.md).
+// CCG_SW_D2: two chunks per trip INTERLEAVED statement by statement in the FP64 role.  Measured on C5: no effect -
+// ptxas serialises the two chains under the register budget (profiles/r02_sweep_experiments.md).  CCG_SW_DU2 (below)
+// is the variant that pays: two chunks per trip one AFTER the other, which only removes the register moves.
 #ifndef CCG_SW_D2
 #define CCG_SW_D2 0
 #endif
@@ -91,8 +91,9 @@ constexpr int kSwStageD = 160;   // floats per stage: the whole block
 constexpr int kSwStageJ = 96;    // floats per stage: X Y Z
 
 // Operand format of the J'J products: 1 = FP16 pairs (u row, v row) per column, mma m16n8k16 (the legacy tensor
-// path issues one m16n8k8 or m16n8k16 per 8.6 cycles and SM sub-partition and shares its pipe with FP64, so half
-// the instructions is half the pipe time; FP16 carries the same 11 significant bits as TF32; the pose columns are
+// path issues one m16n8k8 or m16n8k16 per 8.6 cycles and SM sub-partition whatever the shape, so half the
+// instructions is half the tensor-pipe time - measured 0.845 -> 0.735 ms per C5 launch; FP16 carries the same 11
+// significant bits as TF32; the pose columns are
 // scaled by a power of two so that no entry leaves the FP16 range), 0 = TF32 rows, mma m16n8k8.
 #ifndef CCG_SW_F16
 #define CCG_SW_F16 1

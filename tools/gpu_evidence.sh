@@ -33,6 +33,10 @@ if [[ "$skip" != *" ncu "* ]]; then
     python tools/profile_sweep.py 100000 400 > $o/${tag}_sweep_ncu.log 2>&1
   echo "ncu full exit $?"; tail -2 $o/${tag}_sweep_plain.log
 fi
+if [[ "$skip" != *" ubench "* ]] && [ -x tools/bin/ubench_fp64block ]; then
+  timeout 120 tools/bin/ubench_fp64block > $o/${tag}_ubench_fp64block.txt 2>&1
+  echo "ubench exit $?"; tail -3 $o/${tag}_ubench_fp64block.txt
+fi
 if [[ "$skip" != *" sanit "* ]]; then
   for tool in memcheck racecheck; do
     timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_target.py > $o/${tag}_sanitizer_$tool.log 2>&1

@@ -59,8 +59,10 @@ __device__ __forceinline__ void obs(const K64& K, const double (&R)[9], const do
   gv[2] = fma(pt0, w1, fma(-pt1, w0, gv[2]));
 }
 
-template <int ILP>
-__global__ void __launch_bounds__(256) k_block(double* out, const double* in, int iters) {
+// One warp per SM sub-partition and CTA (128 threads); W CTAs resident per SM give W warps per sub-partition, and
+// __launch_bounds__(128, W) caps the registers accordingly (W = 4: 128 registers, as in the sweep's launch).
+template <int ILP, int W>
+__global__ void __launch_bounds__(128, W) k_block(double* out, const double* in, int iters) {
   K64 K = {in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], in[8]};
   double R[9], t[3];
   for (int i = 0; i < 9; ++i) R[i] = in[9 + i];
@@ -98,34 +100,39 @@ int main() {
   double *din, *dout;
   cudaMalloc(&din, sizeof(h));
   cudaMemcpy(din, h, sizeof(h), cudaMemcpyHostToDevice);
-  cudaMalloc(&dout, sizeof(double) * sms * 1024);
+  cudaMalloc(&dout, sizeof(double) * sms * 1024);  // (4 CTAs x 128 threads per SM at most)
   const int iters = 2048;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  auto run = [&](int ilp, int warps_per_smsp) {
-    const int threads = warps_per_smsp * 4 * 32;  // one CTA per SM
+  auto run = [&](int ilp, int w) {
     auto launch = [&] {
-      if (ilp == 1) k_block<1><<<sms, threads>>>(dout, din, iters);
-      else if (ilp == 2) k_block<2><<<sms, threads>>>(dout, din, iters);
-      else k_block<4><<<sms, threads>>>(dout, din, iters);
+#define CCG_CASE(I, WW) if (ilp == I && w == WW) k_block<I, WW><<<sms * WW, 128>>>(dout, din, iters)
+      CCG_CASE(1, 1); CCG_CASE(1, 2); CCG_CASE(1, 3); CCG_CASE(1, 4);
+      CCG_CASE(2, 1); CCG_CASE(2, 2); CCG_CASE(2, 3); CCG_CASE(2, 4);
+      CCG_CASE(4, 1); CCG_CASE(4, 2);
+#undef CCG_CASE
     };
     launch();
-    cudaDeviceSynchronize();
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+      printf("ILP %d, %d warps/SMSP: launch failed (%s)\n", ilp, w, cudaGetErrorString(err));
+      return;
+    }
     cudaEventRecord(e0);
     launch();
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
+    err = cudaGetLastError();
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    const double obs_per_smsp = (double)warps_per_smsp * iters * ilp;  // warp-observations (32 obs each)
-    printf("ILP %d, %d warps/SMSP: %.1f cycles per 32-observation chunk per SMSP (FP64 pipe floor 176)\n", ilp,
-           warps_per_smsp, ms * 1e-3 * ghz * 1e9 / obs_per_smsp);
+    const double obs_per_smsp = (double)w * iters * ilp;  // warp-observations (32 obs each)
+    printf("ILP %d, %d warps/SMSP: %.1f cycles per 32-observation chunk per SMSP (FP64 pipe floor 176)%s\n", ilp, w,
+           ms * 1e-3 * ghz * 1e9 / obs_per_smsp, err == cudaSuccess ? "" : "  [launch error]");
   };
   for (int ilp : {1, 2, 4})
-    for (int w : {1, 2, 4, 8}) {
-      if (ilp == 4 && w == 8) continue;
-      if (w * 4 * 32 > 1024) continue;
+    for (int w : {1, 2, 3, 4}) {
+      if (ilp == 4 && w > 2) continue;  // (four observations in flight per lane do not fit 128 registers)
       run(ilp, w);
     }
   return 0;
