@@ -366,6 +366,298 @@ k_rig_sweep(RigDev d, double huber_a, double* __restrict__ res_out, double* __re
 }
 
 // --------------------------------------------------------------------------
+// Default rig sweep: FP64 residual, cost and gradient; J'J on the tensor cores.
+//
+// Same split as the single-camera sweep (intr_sweep.cuh): the residual, the robust cost and the gradients
+// g_f, g_c = J'r decide WHERE the LM iteration converges and stay FP64; the Gauss-Newton blocks V_f, W_fc, U_cc =
+// J'J only decide how fast, and per (frame, camera) segment they are one dense contraction
+//     [V W; W' U] = sum over the segment's 2 n residual rows of (row)'(row),   row = [J_frame(6) | J_camera(6)],
+// a 12 x 12 x 2n product that fits one 16 x 16 tile.  One WARP per frame (four per CTA): a lane owns an observation,
+// computes the FP64 geometry once (the all-FP64 kernel computes it in both warps of a pair), accumulates its share of
+// g_f / g_c, rounds the two Jacobian rows to FP16 pairs (u row, v row) per column - 11 significant bits, as TF32;
+// the entries are O(1) in normalised image coordinates, no scaling needed - into a warp-private shared-memory tile, and
+// the warp contracts the 32 observations with 8 mma.sync.m16n8k16 (FP32 accumulation); the A fragment doubles as the
+// B fragment because the product is J'J.  84 + 96 FP64 accumulation FMAs per observation and warp pair become
+// 24, the 90 FP64 accumulators 16 floats, and the kernel needs 130 registers less (more warps per SM).
+// ccg_opts.hessian_fp64 = 1 keeps the all-FP64 kernel (k_rig_sweep), which also serves ccg_rig_eval and the final
+// per-observation cost pass.
+// --------------------------------------------------------------------------
+constexpr int kRtWarps = 4;             // warps (frames in flight) per CTA
+constexpr int kRtRow = 20;              // 32-bit words per tile row: 16 + 4 (conflict-free STS.128 / LDS.64)
+constexpr int kRtTile = 32 * kRtRow;    // words per warp tile: a row per observation
+
+__device__ __forceinline__ unsigned rt_pack(float lo, float hi) {  // (lo, hi) -> f16x2, round to nearest, saturating
+  unsigned r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void rt_mma(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                       unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// candidate frame pose = current (+) (-z - Y du), all 32 lanes: lane j takes column j of Y (the one-lane-per-row
+// version of frame_prologue walks 6 C dependent loads per row)
+__device__ __forceinline__ void frame_prologue_warp(const RigDev& d, int par, int64_t f, int lane, const double* s_du,
+                                                    int n6, double (&R)[9], double (&t)[3], double& gTd, double& dDd) {
+  const double* yz = d.yz + (size_t)f * d.yz_stride;
+  double part[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) part[a] = 0.0;
+  for (int j = lane; j < n6; j += 32) {
+    const double duj = s_du[j];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) part[a] = fma(yz[a * n6 + j], duj, part[a]);
+  }
+  double r = group_reduce<8, double>(part, lane & 7);
+  r += __shfl_xor_sync(0xffffffffu, r, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 16);
+  double dl = 0.0;
+  if (lane < 6) {
+    dl = -yz[6 * n6 + lane] - r;
+    gTd += yz[6 * n6 + 6 + lane] * dl;
+    dDd += dl * dl * yz[6 * n6 + 12 + lane];
+  }
+  const double d0 = __shfl_sync(0xffffffffu, dl, 0), d1 = __shfl_sync(0xffffffffu, dl, 1),
+               d2 = __shfl_sync(0xffffffffu, dl, 2), d3 = __shfl_sync(0xffffffffu, dl, 3),
+               d4 = __shfl_sync(0xffffffffu, dl, 4), d5 = __shfl_sync(0xffffffffu, dl, 5);
+  const double* pc = d.pose[par] + (size_t)f * 8;
+  double q[4] = {pc[0], pc[1], pc[2], pc[3]};
+  double qn[4];
+  quat_plus(q, d0, d1, d2, qn);
+  t[0] = pc[4] + d3;
+  t[1] = pc[5] + d4;
+  t[2] = pc[6] + d5;
+  if (lane < 7) {
+    double* pn = d.pose[par ^ 1] + (size_t)f * 8;
+    const double val = lane == 0 ? qn[0] : lane == 1 ? qn[1] : lane == 2 ? qn[2] : lane == 3 ? qn[3]
+                     : lane == 4 ? t[0] : lane == 5 ? t[1] : t[2];
+    pn[lane] = val;
+  }
+  quat_to_rot(qn, R);
+}
+
+__global__ void __launch_bounds__(kRtWarps * 32, 2) k_rig_sweep_tc(RigDev d, double huber_a) {
+  __shared__ double s_cam[kMaxCams][12];
+  __shared__ double s_du[kMaxN6];
+  __shared__ double s_acc[kRtWarps][kMaxCams][27];  // per warp: U_cc 21 | g_c 6
+  __shared__ double s_sc[kRtWarps][8];
+  __shared__ __align__(16) unsigned s_tile[kRtWarps][kRtTile];
+  __shared__ int s_meta[2];
+  const WorkItem it = d.items[blockIdx.x];
+  RigState& ps = d.ps[0];
+  const int C = d.n_cams, n6 = 6 * C;
+  if (threadIdx.x == 0) {
+    s_meta[0] = ps.lm.par;
+    s_meta[1] = (ps.lm.status == 0 && ps.lm.solve_ok) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_meta[1]) return;
+  const int par = s_meta[0];
+  if (threadIdx.x < C) {
+    double q[4] = {ps.cam[par ^ 1][threadIdx.x][0], ps.cam[par ^ 1][threadIdx.x][1], ps.cam[par ^ 1][threadIdx.x][2],
+                   ps.cam[par ^ 1][threadIdx.x][3]};
+    double R[9];
+    quat_to_rot(q, R);
+    for (int i = 0; i < 9; ++i) s_cam[threadIdx.x][i] = R[i];
+    for (int i = 0; i < 3; ++i) s_cam[threadIdx.x][9 + i] = ps.cam[par ^ 1][threadIdx.x][4 + i];
+  }
+  if (threadIdx.x < n6) s_du[threadIdx.x] = ps.du[threadIdx.x];
+  for (int i = threadIdx.x; i < kRtWarps * kMaxCams * 27; i += blockDim.x) (&s_acc[0][0][0])[i] = 0.0;
+  for (int i = threadIdx.x; i < kRtWarps * kRtTile; i += blockDim.x) (&s_tile[0][0])[i] = 0u;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const unsigned tile = (unsigned)__cvta_generic_to_shared(&s_tile[warp][0]);
+  const unsigned row_w = tile + (unsigned)lane * (kRtRow * 4);                  // this lane's observation row
+  const unsigned frag = tile + (unsigned)(2 * tig * kRtRow + 2 * g) * 4;       // its fragment of k-step 0
+  // where this lane's eight product elements go: element i = (n-block i >> 2, slot i & 3) is (row, col) with
+  // row = g (+ 8), col = 8 (i >> 2) + 2 tig (+ 1).  kind 1: V (upper), 2: W, 3: U (upper); ofs as used below.
+  int kind[8], ofs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = i & 3, row = g + ((e & 2) ? 8 : 0), col = (i >> 2) * 8 + 2 * tig + (e & 1);
+    kind[i] = 0;
+    ofs[i] = 0;
+    if (row < 6 && col < 6 && col >= row) {
+      kind[i] = 1;
+      ofs[i] = row * 6 - row * (row - 1) / 2 + (col - row);
+    } else if (row < 6 && col >= 6 && col < 12) {
+      kind[i] = 2;
+      ofs[i] = 27 + row * n6 + (col - 6);
+    } else if (row >= 6 && row < 12 && col >= row && col < 12) {
+      const int a = row - 6, b = col - 6;
+      kind[i] = 3;
+      ofs[i] = a * 6 - a * (a - 1) / 2 + (b - a);
+    }
+  }
+  double rho_sum = 0.0, sumsq = 0.0, nobs = 0.0, gTd = 0.0, dDd = 0.0;
+
+  for (int64_t f = it.v0 + warp; f < it.v1; f += kRtWarps) {
+    double Rf[9], tf[3];
+    frame_prologue_warp(d, par, f, lane, s_du, n6, Rf, tf, gTd, dDd);
+    double* blk = d.blk[par ^ 1] + (size_t)f * d.blk_stride;
+    double gf[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gf[i] = 0.0;
+    float vsum[2] = {0.f, 0.f};  // V elements of this lane (slots 0, 1 of n-block 0), summed over the cameras
+    int64_t o0 = d.seg_off[f * C], o1 = d.seg_off[f * C + 1];
+    int ip_a = 0, ip_b = 0;
+    float mu_n = 0.f, mv_n = 0.f;
+    auto prime_ids = [&](int64_t a0, int64_t a1) {
+      if (a0 < a1) {
+        const int64_t oa = min(a0 + lane, a1 - 1), ob = min(a0 + lane + 32, a1 - 1);
+        ip_a = __ldg(d.pt + oa);
+        ip_b = __ldg(d.pt + ob);
+        mu_n = __ldg(d.u + oa);
+        mv_n = __ldg(d.v + oa);
+      }
+    };
+    prime_ids(o0, o1);
+    for (int c = 0; c < C; ++c) {
+      double Rc[9], tc[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rc[i] = s_cam[c][i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tc[i] = s_cam[c][9 + i];
+      const int64_t o2 = c + 1 < C ? d.seg_off[f * C + c + 2] : o1;
+      double gc[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) gc[i] = 0.0;
+      float c0a[4] = {0.f, 0.f, 0.f, 0.f}, c0b[4] = {0.f, 0.f, 0.f, 0.f};
+      float c1a[4] = {0.f, 0.f, 0.f, 0.f}, c1b[4] = {0.f, 0.f, 0.f, 0.f};
+      float Xn = 0.f, Yn = 0.f, Zn = 0.f;
+      int ip_nn = ip_b;
+      if (o0 < o1) {
+        Xn = __ldg(d.Xw + 3 * (size_t)ip_a);
+        Yn = __ldg(d.Xw + 3 * (size_t)ip_a + 1);
+        Zn = __ldg(d.Xw + 3 * (size_t)ip_a + 2);
+      }
+      auto fetch = [&](int64_t o, int& ip_next, float& mu, float& mv, float& Xf, float& Yf, float& Zf) {
+        const int64_t on = min(o + 32, o1 - 1), onn = min(o + 64, o1 - 1);
+        const int ip1 = ip_next;
+        ip_next = __ldg(d.pt + onn);
+        mu = __ldg(d.u + on);
+        mv = __ldg(d.v + on);
+        Xf = __ldg(d.Xw + 3 * (size_t)ip1);
+        Yf = __ldg(d.Xw + 3 * (size_t)ip1 + 1);
+        Zf = __ldg(d.Xw + 3 * (size_t)ip1 + 2);
+      };
+      // one step: 32 observations, lane's own at o (valid or padding)
+      auto step = [&](int64_t o, float mu, float mv, float Xf, float Yf, float Zf) {
+        const bool valid = o < o1;
+        RigGeom gm;
+        rig_geometry(Rf, tf, Rc, tc, (double)Xf, (double)Yf, (double)Zf, (double)mu, (double)mv, huber_a, gm);
+        const double ru = valid ? gm.ru : 0.0, rv = valid ? gm.rv : 0.0;
+        rho_sum += valid ? gm.rho : 0.0;
+        sumsq += valid ? gm.s : 0.0;
+        nobs += valid ? 1.0 : 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          gf[a] = fma(gm.jfu[a], ru, fma(gm.jfv[a], rv, gf[a]));
+          gc[a] = fma(gm.jcu[a], ru, fma(gm.jcv[a], rv, gc[a]));
+        }
+        // tile row: product column m (0..5 frame, 6..11 camera, 12..15 zero) at word (m % 8) * 2 + m / 8
+        const float vz = valid ? 1.0f : 0.0f;
+        unsigned w[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const int pos = (m % 8) * 2 + m / 8;
+          if (m < 6) w[pos] = rt_pack((float)gm.jfu[m] * vz, (float)gm.jfv[m] * vz);
+          else if (m < 12) w[pos] = rt_pack((float)gm.jcu[m - 6] * vz, (float)gm.jcv[m - 6] * vz);
+          else w[pos] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_w + 16 * i), "r"(w[4 * i]), "r"(w[4 * i + 1]),
+                       "r"(w[4 * i + 2]), "r"(w[4 * i + 3])
+                       : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          unsigned a0, a1, a2, a3;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(frag + (8 * s) * kRtRow * 4) : "memory");
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a2), "=r"(a3) : "r"(frag + (8 * s + 1) * kRtRow * 4) : "memory");
+          if (s & 1) {
+            rt_mma(c0b, a0, a1, a2, a3, a0, a2);
+            rt_mma(c1b, a0, a1, a2, a3, a1, a3);
+          } else {
+            rt_mma(c0a, a0, a1, a2, a3, a0, a2);
+            rt_mma(c1a, a0, a1, a2, a3, a1, a3);
+          }
+        }
+        __syncwarp();
+      };
+      {
+        float mu_b = 0.f, mv_b = 0.f, Xb = 0.f, Yb = 0.f, Zb = 0.f;
+        for (int64_t base = o0; base < o1; base += 64) {
+          const int64_t o = base + lane;
+          fetch(min(o, o1 - 1), ip_nn, mu_b, mv_b, Xb, Yb, Zb);
+          step(o, mu_n, mv_n, Xn, Yn, Zn);
+          if (base + 32 >= o1) break;
+          fetch(min(o + 32, o1 - 1), ip_nn, mu_n, mv_n, Xn, Yn, Zn);
+          step(o + 32, mu_b, mv_b, Xb, Yb, Zb);
+        }
+      }
+      o0 = o1;
+      o1 = o2;
+      if (c + 1 < C) prime_ids(o0, o1);
+      // ---- per-segment epilogue
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float val = (i >> 2) == 0 ? c0a[i & 3] + c0b[i & 3] : c1a[i & 3] + c1b[i & 3];
+        if (i < 2) vsum[i] += val;
+        if (kind[i] == 2) blk[ofs[i] + 6 * c] = (double)val;
+        if (kind[i] == 3) s_acc[warp][c][ofs[i]] += (double)val;  // one owner lane per element
+      }
+      {
+        double tmp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tmp[i] = i < 6 ? gc[i] : 0.0;
+        double r = group_reduce<8, double>(tmp, lane & 7);
+        r += __shfl_xor_sync(0xffffffffu, r, 8);
+        r += __shfl_xor_sync(0xffffffffu, r, 16);
+        if (lane < 6) s_acc[warp][c][21 + lane] += r;
+      }
+    }
+    // ---- per-frame epilogue: V_f (upper triangle) and g_f
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (kind[i] == 1) blk[ofs[i]] = (double)vsum[i];
+    {
+      double tmp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tmp[i] = i < 6 ? gf[i] : 0.0;
+      double r = group_reduce<8, double>(tmp, lane & 7);
+      r += __shfl_xor_sync(0xffffffffu, r, 8);
+      r += __shfl_xor_sync(0xffffffffu, r, 16);
+      if (lane < 6) blk[21 + lane] = r;
+    }
+  }
+  {
+    double tmp[8] = {rho_sum, sumsq, gTd, dDd, nobs, 0.0, 0.0, 0.0};
+    double r = group_reduce<8, double>(tmp, lane & 7);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    if (lane < 8) s_sc[warp][lane] = lane < 5 ? r : 0.0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < kRigPart; c += blockDim.x) {
+    double s = 0.0;
+    if (c < 27 * kMaxCams) {
+      const int cam = c / 27, e = c - 27 * cam;
+      if (cam < C)
+        for (int p = 0; p < kRtWarps; ++p) s += s_acc[p][cam][e];
+    } else if (c < 27 * kMaxCams + 5) {
+      for (int p = 0; p < kRtWarps; ++p) s += s_sc[p][c - 27 * kMaxCams];
+    }
+    d.sweep_part[(size_t)blockIdx.x * kRigPart + c] = s;
+  }
+}
+
+// --------------------------------------------------------------------------
 // frame elimination, one warp per frame; a lane owns the columns lane, lane + 32, ... of [W | g_f]
 // (6C + 1 columns).  The frame's columns are staged in shared memory so that every lane can read
 // column i for the products (W'Y)[i][j]; the warp's share of the reduced system accumulates in
@@ -1017,7 +1309,8 @@ int rig_sweep_decide(ccg_rig_problem* p, const LmParams& P, Profiler& prof, doub
   RigDev& d = p->dev;
   cudaStream_t st = ctx->stream;
   prof.begin(TAG_SWEEP);
-  k_rig_sweep<<<p->n_items, kRigWarps * 32, 0, st>>>(d, P.huber_a, res_out, nullptr);
+  if (P.hessian_fp64 == 0 && !res_out) k_rig_sweep_tc<<<p->n_items, kRtWarps * 32, 0, st>>>(d, P.huber_a);
+  else k_rig_sweep<<<p->n_items, kRigWarps * 32, 0, st>>>(d, P.huber_a, res_out, nullptr);
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
@@ -1275,6 +1568,7 @@ int ccg_rig_eval(ccg_ctx* ctx, const float* u, const float* v, const int32_t* ob
     ccg_opts o;
     ccg_default_opts(&o);
     o.huber_a = huber_a;
+    o.hessian_fp64 = 1;  // the evaluation entry returns the exact (all-FP64) blocks
     const LmParams P = to_params(o);
     CCG_TRY(rig_reset(p, P));
     double* d_res = nullptr;

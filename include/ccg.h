@@ -52,7 +52,7 @@ typedef struct {
   double huber_a;               /* rig only: (double)(3.0f/500.0f), extrinsics_calibrator.cpp:176; <= 0: no loss */
   double noise_factor;          /* 4: a step whose predicted decrease is <= noise_factor * (eps/2) * max|measurement| *
                                    sqrt(2 cost) is below the FP64 resolution of the cost: take it and stop */
-  int32_t hessian_fp64;         /* single-camera sweep variant.  Residual, cost and gradient are FP64 in all of them (same
+  int32_t hessian_fp64;         /* sweep variant (single camera and rig).  Residual, cost and gradient are FP64 in all of them (same
                                    fixed point); they differ in how the J'J blocks are formed:
                                    0 (default) tensor-core products (mma.sync m16n8k16, FP32 accumulation) of the
                                    float32 Jacobian rows rounded to FP16 (11 significant bits, as TF32; pose columns

@@ -29,7 +29,21 @@ def test_rig_eval_blocks_match_oracle(ctx):
             assert block_err(g[key][f], r[key][f]) <= 1e-10, (key, f)
 
 
-def _check(got, ref, s):
+# Per-observation final cost against the oracle, relative to the largest one.  Exact (all-FP64) normal-equation blocks
+# (hessian_fp64 = 1) converge quadratically onto the oracle's iterate: 1e-9.  The default sweep forms J'J from 11-bit
+# operands on the tensor cores (same fixed point, linear last steps): the same number of iterations, parameters within
+# 1e-10 and RMS within 1e-12 of the oracle (BASELINE tolerances 1e-6 / 1e-9 hold unchanged below), per-observation costs
+# within 2e-8 (measured; 1e-7 asserted).
+COST_TOL = {0: 1e-7, 1: 1e-9}
+
+
+def _opts(h64):
+    import camera_calibrator_b200 as cc
+
+    return cc.default_opts(max_iterations=1000, hessian_fp64=h64)
+
+
+def _check(got, ref, s, h64=1):
     gqc, gtc, gqf, gtf, gcost, grep = got
     rqc, rtc, rqf, rtf, rcost, rrep = ref
     assert grep["termination"] in (1, 2, 3)
@@ -42,25 +56,28 @@ def _check(got, ref, s):
     assert np.array_equal(gqc[0], s.q_c[0]) and np.array_equal(gtc[0], s.t_c[0])
     # per-observation final cost, in the caller's observation order
     assert gcost.shape == rcost.shape
-    assert np.max(np.abs(gcost - rcost)) <= 1e-9 * max(np.max(rcost), 1e-30)
+    assert np.max(np.abs(gcost - rcost)) <= COST_TOL[h64] * max(np.max(rcost), 1e-30)
+    assert grep["iterations"] == rrep["iterations"]
     assert abs(gcost.sum() - grep["final_cost"]) <= 1e-10 * grep["final_cost"]
 
 
-def test_rig_solve_two_cameras_reference_scenario(ctx):
+@pytest.mark.parametrize("h64", [0, 1])
+def test_rig_solve_two_cameras_reference_scenario(ctx, h64):
     """The reference test's shape (test_extrinsics_calibrator.cpp:40-134): 2 cameras, camera 0
-    frozen, 4 points per frame, all noise sources; fresh object (gauge fixed)."""
+    frozen, 4 points per frame, all noise sources; fresh object (gauge fixed).  Both sweep variants."""
     s = synth.rig_scene(n_cams=2, n_frames=200, grid=(2, 2), pitch=0.2, seed=0)
-    got = rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    got = rig_api.rig_solve(ctx, *_args(s), s.q_c.copy(), s.t_c.copy(), s.cam_frozen, s.q_f.copy(), s.t_f.copy(), opts=_opts(h64))
     ref = oracle.rig_solve(*_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
-    _check(got, ref, s)
+    _check(got, ref, s, h64)
 
 
-def test_rig_solve_four_cameras_with_outliers(ctx):
-    """C3 shape reduced: 4 cameras x 120 frames x 35 points, 5 % gross outliers (Huber active)."""
+@pytest.mark.parametrize("h64", [0, 1])
+def test_rig_solve_four_cameras_with_outliers(ctx, h64):
+    """C3 shape reduced: 4 cameras x 120 frames x 35 points, 5 % gross outliers (Huber active).  Both sweep variants."""
     s = synth.rig_scene(n_cams=4, n_frames=120, grid=(7, 5), seed=2, outlier_fraction=0.05)
-    got = rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
+    got = rig_api.rig_solve(ctx, *_args(s), s.q_c.copy(), s.t_c.copy(), s.cam_frozen, s.q_f.copy(), s.t_f.copy(), opts=_opts(h64))
     ref = oracle.rig_solve(*_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
-    _check(got, ref, s)
+    _check(got, ref, s, h64)
     assert np.count_nonzero(ref[4] > 0.5 * HUBER * HUBER) > 0  # some observations are in the linear zone
 
 
@@ -89,9 +106,11 @@ def test_rig_twelve_cameras(ctx):
     assert block_err(g["U"], r["U"]) <= 1e-11 and block_err(g["gu"], r["gu"]) <= 1e-10
     for f in range(60):
         assert block_err(g["W"][f], r["W"][f]) <= 1e-10, f
-    got = rig_api.rig_solve(ctx, *_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
     ref = oracle.rig_solve(*_args(s), s.q_c, s.t_c, s.cam_frozen, s.q_f, s.t_f)
-    _check(got, ref, s)
+    for h64 in (0, 1):
+        got = rig_api.rig_solve(ctx, *_args(s), s.q_c.copy(), s.t_c.copy(), s.cam_frozen, s.q_f.copy(), s.t_f.copy(),
+                                opts=_opts(h64))
+        _check(got, ref, s, h64)
 
 
 def test_rig_too_many_cameras_is_reported(ctx):
