@@ -48,7 +48,7 @@ struct ccg_ctx {
   // (cudaMalloc/cudaFree of the ~1 GB of a large calibration cost more than its whole LM loop)
   cudaMemPool_t pool = nullptr;
   // per-device opt-in of the default sweep's dynamic shared memory ([RES variant])
-  bool sweep_attr[2] = {false, false};
+  bool sweep_attr[4] = {false, false, false, false};
   bool lm_attr = false;              // the same for the persistent LM kernel
 };
 
@@ -82,10 +82,23 @@ struct PeerSlot {
   unsigned long long seq;
   unsigned long long pad[7];
 };
+// The rig's reduced system is 6C x 6C (plus right-hand side and two scalars): a second set of slots of kPeerBigVals
+// doubles behind the small ones in the same mailbox allocation (same protocol, same sequence counter).
+constexpr int kPeerBigVals = 96 * 96 + 96 + 32;
+struct PeerBigSlot {
+  double data[kPeerBigVals];
+  unsigned long long seq;
+  unsigned long long pad[7];
+};
+constexpr size_t kPeerSmallBytes = sizeof(PeerSlot) * 2 * kPeerMaxWorld;
+constexpr size_t kPeerMailboxBytes = kPeerSmallBytes + sizeof(PeerBigSlot) * 2 * kPeerMaxWorld;
 struct PeerComm {
   PeerSlot* box[kPeerMaxWorld];  // box[p] = rank p's mailbox: PeerSlot[2][kPeerMaxWorld]
   unsigned long long* seq;       // this rank's counter of completed allreduces
   int rank, world;
+  __host__ __device__ PeerBigSlot* big(int p) const {
+    return reinterpret_cast<PeerBigSlot*>(reinterpret_cast<unsigned char*>(box[p]) + kPeerSmallBytes);
+  }
 };
 PeerComm peer_comm(const ccg_ctx* ctx);
 
@@ -381,6 +394,52 @@ __device__ inline void peer_allreduce64(double* s_vals, const PeerComm& pc) {
   }
   __syncthreads();
   if (tid == 0) *pc.seq = seq;
+}
+
+// The same for n <= kPeerBigVals values in shared OR global memory (the rig's reduced systems), called by all
+// threads of ONE CTA of any size.  Returns false (and poisons vals with NaN) when a peer did not show up.
+__device__ inline bool peer_allreduce_n(double* vals, int n, const PeerComm& pc) {
+  __shared__ unsigned long long s_seq_n;
+  __shared__ int s_timeout_n;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) {
+    s_seq_n = *pc.seq + 1ull;
+    s_timeout_n = 0;
+  }
+  __syncthreads();
+  const unsigned long long seq = s_seq_n;
+  const int par = (int)(seq & 1ull);
+  for (int i = tid; i < n; i += nt) {
+    const double val = vals[i];
+    for (int p = 0; p < pc.world; ++p) pc.big(p)[par * kPeerMaxWorld + pc.rank].data[i] = val;
+  }
+  __syncthreads();
+  if (tid < pc.world) {
+    __threadfence_system();
+    unsigned long long* flag = &pc.big(tid)[par * kPeerMaxWorld + pc.rank].seq;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    const unsigned long long* mine = &pc.big(pc.rank)[par * kPeerMaxWorld + tid].seq;
+    const long long t0 = clock64();
+    unsigned long long got = 0ull;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
+      if (got == seq) break;
+      if (clock64() - t0 > 60000000000ll) {
+        s_timeout_n = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const bool ok = s_timeout_n == 0;
+  for (int i = tid; i < n; i += nt) {
+    double acc = 0.0;
+    for (int src = 0; src < pc.world; ++src) acc += __ldcg(&pc.big(pc.rank)[par * kPeerMaxWorld + src].data[i]);
+    vals[i] = ok ? acc : nan("");
+  }
+  __syncthreads();
+  if (tid == 0) *pc.seq = seq;
+  return ok;
 }
 
 // --------------------------------------------------------------------------

@@ -123,7 +123,7 @@ PeerComm peer_comm(const ccg_ctx* ctx) {
 static void setup_peer_mailboxes(ccg_ctx* ctx) {
   ctx->peer_ok = false;
   if (getenv("CCG_NO_PEER") || ctx->world > kPeerMaxWorld || !g_nccl.AllGather) return;
-  const size_t bytes = sizeof(PeerSlot) * 2 * kPeerMaxWorld;
+  const size_t bytes = kPeerMailboxBytes;  // small slots (single camera) + big slots (rig)
   unsigned char* d_h = nullptr;
   auto fail = [&]() {
     cudaGetLastError();

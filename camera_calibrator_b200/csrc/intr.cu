@@ -1129,14 +1129,23 @@ int reset_problem(ccg_intr_problem* p, const LmParams& P) {
 
 enum { TAG_SWEEP = 0, TAG_SCHUR = 1, TAG_SMALL = 2 };
 
+template <bool RES, int PAIRS>
+void launch_sweep_ws_tp(ccg_intr_problem* p, double* res_out) {
+  ccg_ctx* ctx = p->ctx;
+  constexpr int slot = (RES ? 1 : 0) + (PAIRS == 4 ? 2 : 0);
+  if (!ctx->sweep_attr[slot]) {  // per context: the attribute is per device
+    // (no carveout preference: with cudaSharedmemCarveoutMaxShared the few spilled registers of the roles lose their
+    // L1 and the launch is 8 % slower - measured)
+    cudaFuncSetAttribute(k_intr_sweep_ws<RES, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem_bytes(PAIRS));
+    ctx->sweep_attr[slot] = true;
+  }
+  k_intr_sweep_ws<RES, PAIRS><<<p->n_items, 64 * PAIRS, sw_smem_bytes(PAIRS), ctx->stream>>>(p->dev, res_out);
+}
 template <bool RES>
 void launch_sweep_ws_t(ccg_intr_problem* p, double* res_out) {
-  ccg_ctx* ctx = p->ctx;
-  if (!ctx->sweep_attr[RES ? 1 : 0]) {  // per context: the attribute is per device
-    cudaFuncSetAttribute(k_intr_sweep_ws<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmem);
-    ctx->sweep_attr[RES ? 1 : 0] = true;
-  }
-  k_intr_sweep_ws<RES><<<p->n_items, kSwThreads, kSwSmem, ctx->stream>>>(p->dev, res_out);
+  // a batch of one-CTA problems: two CTAs of 4 warp pairs per SM (see kSwPairs in intr_sweep.cuh)
+  if (p->single_item) launch_sweep_ws_tp<RES, 4>(p, res_out);
+  else launch_sweep_ws_tp<RES, 8>(p, res_out);
 }
 
 // one residual+Jacobian sweep followed by the accept/reject step

@@ -194,7 +194,7 @@ struct LmJob {
 // IS_D: the calling warp's role (the loop is instantiated once per role).
 template <bool IS_D>
 __device__ __forceinline__ bool lm_sweep_decide(const IntrDev& d, const LmParams& P, const PeerComm& pc, const LmJob& job,
-                                                LmCta& s, const SwSmem& sm, IntrState& ps) {
+                                                LmCta& s, const SwSmem<kSwPairs>& sm, IntrState& ps) {
   LmState& lm = *reinterpret_cast<LmState*>(s.head);
   const int tid = threadIdx.x;
   const bool evaluate = lm.status == 0 && lm.solve_ok != 0;
@@ -203,7 +203,7 @@ __device__ __forceinline__ bool lm_sweep_decide(const IntrDev& d, const LmParams
     const int par = lm.par;
     if (tid < 9) s.k[tid] = s.intr[par ^ 1][tid];
     __syncthreads();
-    sw_sweep_item<false, IS_D ? 1 : 2>(d, job.it, par, s.k, s.du, sm, s.red, s.step,
+    sw_sweep_item<false, IS_D ? 1 : 2, kSwPairs>(d, job.it, par, s.k, s.du, sm, s.red, s.step,
                                        d.sweep_part + (size_t)job.item * kSweepPart, nullptr);
     alive = lm_grid_barrier<IS_D>(job.ctl, s, job.n_ctas);
     if (alive) {
@@ -273,7 +273,7 @@ __device__ __forceinline__ bool lm_schur_solve(const IntrDev& d, const LmParams&
 // the LM loop of the problem, as run by the warps of one role
 template <bool IS_D>
 __device__ __forceinline__ void lm_role_loop(const IntrDev& d, const LmParams& P, const PeerComm& pc, int reduce_mode,
-                                             LmCtl* ctl, double* lm_schur_part, LmCta& s, const SwSmem& sm) {
+                                             LmCtl* ctl, double* lm_schur_part, LmCta& s, const SwSmem<kSwPairs>& sm) {
   const int tid = threadIdx.x;
   IntrState& ps = d.ps[0];
   LmJob job;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kSwThreads, 1)
 k_intr_lm(IntrDev d, LmParams P, PeerComm pc, int reduce_mode, LmCtl* ctl, double* lm_schur_part) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ LmCta s;
-  const SwSmem sm(s_dyn);
+  const SwSmem<kSwPairs> sm(s_dyn);
   if (threadIdx.x == kLmLeader) s.epoch = 0ull;
   if ((threadIdx.x >> 5) >= kSwPairs) {
     if (kSwRegD > kSwRegLaunch) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSwRegD));

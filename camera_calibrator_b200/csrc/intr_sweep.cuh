@@ -41,14 +41,20 @@
 
 namespace ccg {
 
-constexpr int kSwPairs = 8;              // (FP64 warp, Jacobian warp) pairs per CTA, two per SM sub-partition
-constexpr int kSwWarps = 2 * kSwPairs;   // warps 0 .. kSwPairs-1: Jacobian role; the rest: FP64 role
+// (FP64 warp, Jacobian warp) pairs per CTA: a template parameter PAIRS of everything below.  An SM always holds 8
+// pairs, two per SM sub-partition: ONE CTA of 8 pairs or TWO CTAs of 4 pairs (one warpgroup per role, which is what
+// setmaxnreg needs).  Two smaller CTAs overlap one CTA's latency-bound prologue and epilogue (LM state, candidate
+// poses, first blocks of the streams, final reduction) with the other's streaming - what a batch of 50-view problems,
+// one CTA each, spends most of its time on (C4: 0.59 -> 0.48 ms per sweep launch); a big problem with hundreds of
+// views per CTA is 2 % faster with one CTA of 8 pairs (build_problem chooses).
+constexpr int kSwPairs = 8;              // the larger configuration (the persistent LM kernel uses it)
+constexpr int kSwWarps = 2 * kSwPairs;   // warps 0 .. PAIRS-1: Jacobian role; the rest: FP64 role
 constexpr int kSwThreads = kSwWarps * 32;
-// register budgets: the CTA is launched with 128 registers per thread; the Jacobian warpgroups give
-// registers back (setmaxnreg.dec) and the FP64 warpgroups take them (.inc)
+// register budgets: the CTA is launched with 128 registers per thread (8 pairs per SM in either configuration); the
+// Jacobian warpgroups give registers back (setmaxnreg.dec) and the FP64 warpgroups take them (.inc)
 constexpr int kSwRegLaunch = (65536 / kSwThreads) & ~7;
 #ifndef CCG_SW_REGJ
-#define CCG_SW_REGJ 104
+#define CCG_SW_REGJ 88
 #endif
 constexpr int kSwRegJ = CCG_SW_REGJ;
 constexpr int kSwRegD = 2 * kSwRegLaunch - kSwRegJ;
@@ -99,8 +105,18 @@ constexpr int kSwStageJ = 96;    // floats per stage: X Y Z
 #define CCG_SW_F16 1
 #endif
 constexpr bool kSwF16 = CCG_SW_F16 != 0;
-constexpr int kTcRow = 20;            // 32-bit words per tile row (16 + 4: conflict-free STS.128 and LDS.64)
-constexpr int kTcTile = (kSwF16 ? 32 : 64) * kTcRow;  // one 32-observation tile: a row per observation (FP16 pairs) or per residual
+// CCG_SW_LDSM (FP16 operands only): fragments by ldmatrix instead of LDS.64.  The product is J'J, so the B fragments of a
+// k-step are the A fragment's registers regrouped - (a0, a2) and (a1, a3) - but HMMA wants each operand in consecutive
+// registers, and ptxas pays two MOVs per HMMA for the regrouping (16 of the role's 193 instructions per chunk).  Two
+// ldmatrix.x4.trans of the same eight 8 x 8 blocks, the second with the blocks in B order, deliver both groupings
+// directly.  Tile: a row per RESIDUAL (u rows 0..31, v rows 32..63), 16 FP16 in natural column order, row stride 48 B
+// (conflict-free for the lane's two STS.128 per row and for the eight row addresses of a block).
+#ifndef CCG_SW_LDSM
+#define CCG_SW_LDSM 1
+#endif
+constexpr bool kSwLdsm = kSwF16 && CCG_SW_LDSM != 0;
+constexpr int kTcRow = kSwLdsm ? 12 : 20;  // 32-bit words per tile row (LDS.64 layout: 16 + 4, conflict-free STS.128 and LDS.64)
+constexpr int kTcTile = ((kSwF16 && !kSwLdsm) ? 32 : 64) * kTcRow;  // one 32-observation tile: a row per observation (FP16 pairs) or per residual
 
 // The Jacobian warp of a pair is the faster one; left alone it runs ahead of its FP64 partner by more than L2 holds
 // (all pairs of the GPU together), and every block is then fetched from HBM twice (measured: 1.70 x the algorithmic
@@ -109,9 +125,12 @@ constexpr int kTcTile = (kSwF16 ? 32 : 64) * kTcRow;  // one 32-observation tile
 #define CCG_SW_LEAD 0
 #endif
 constexpr int kSwLead = CCG_SW_LEAD;
-constexpr size_t kSwSmem = sizeof(int) * 16 + sizeof(double) * kSwWarps * kSweepPart +
-                           sizeof(float) * kSwPairs * (kSwStagesD * kSwStageD + kSwStagesJ * kSwStageJ + kSwTiles * kTcTile);
-static_assert(kSwSmem <= 227 * 1024, "shared memory");
+constexpr size_t sw_smem_bytes(int pairs) {
+  return sizeof(int) * 16 + sizeof(double) * 2 * pairs * kSweepPart +
+         sizeof(float) * pairs * (kSwStagesD * kSwStageD + kSwStagesJ * kSwStageJ + kSwTiles * kTcTile);
+}
+constexpr size_t kSwSmem = sw_smem_bytes(kSwPairs);
+static_assert(kSwSmem <= 227 * 1024 && 2 * (sw_smem_bytes(4) + 1024) <= 227 * 1024, "shared memory");
 static_assert(kSwTail == 0 || kSwTiles * kTcTile >= kSwStagesD * kSwStageD, "the FP64 tail's ring lives in the tile(s)");
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], unsigned a0, unsigned a1, unsigned a2,
@@ -196,12 +215,13 @@ __device__ __forceinline__ void tc_fp64_observation(const TcConst64& K, const do
   const double pt2 = fma(R[6], X, fma(R[7], Y, fma(R[8], Z, t[2])));
   const double iz = fast_rcp(pt2);
   const double xn = pt0 * iz, yn = pt1 * iz;
-  const double xx = xn * xn, yy = yn * yn, xy = xn * yn;
-  const double r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
+  const double tx = xn + xn, ty = yn + yn;
+  const double r2 = fma(xn, xn, yn * yn), r4 = r2 * r2, r6 = r4 * r2;
   // m = 1 + k1 r2 + k2 r4 + k3 r6 and mp = dm/dr2 by Horner (no derived constants to keep in registers)
   const double h2 = fma(r2, K.k3, K.k2), h1 = fma(r2, h2, K.k1);
   const double m = fma(r2, h1, 1.0), mp = fma(r2, fma(r2, K.k3, h2), h1);
-  const double a1 = xy + xy, a2 = fma(2.0, xx, r2), a3 = fma(2.0, yy, r2);
+  // a1 = 2 xn yn, a2 = r2 + 2 xn^2, a3 = r2 + 2 yn^2 through tx = 2 xn, ty = 2 yn (the reverse pass needs them anyway)
+  const double a1 = tx * yn, a2 = fma(tx, xn, r2), a3 = fma(ty, yn, r2);
   const double xd = fma(xn, m, fma(K.p1, a1, K.p2 * a2));
   const double yd = fma(yn, m, fma(K.p2, a1, K.p1 * a3));
   double ru = fma(K.fx, xd, K.cx - dmu);
@@ -230,7 +250,6 @@ __device__ __forceinline__ void tc_fp64_observation(const TcConst64& K, const do
   gu[7] = fma(a2, tu, fma(a1, tv, gu[7]));
   // d(xd,yd)/d(xn,yn): F00 = m + 2xx mp + 2p1 yn + 6p2 xn, F01 = a1 mp + 2p1 xn + 2p2 yn,
   // F11 = m + 2yy mp + 2p2 xn + 6p1 yn
-  const double tx = xn + xn, ty = yn + yn;
   const double u1 = K.p1 * ty, u2 = K.p2 * tx, base = m + (u1 + u2);
   const double F00 = fma(2.0, u2, fma(a2 - r2, mp, base));
   const double F01 = fma(a1, mp, fma(K.p1, tx, K.p2 * ty));
@@ -400,7 +419,7 @@ __device__ __forceinline__ void tc_store_rows(unsigned row_u, const float4 (&ur)
 // depth of the dependent HMMA chain.  FULL: all 32 observations are valid.  frag = shared address
 // of element (row 2 tig, float 2 g) of the tile.
 template <bool FULL>
-__device__ __forceinline__ void tc_contract(unsigned frag, int nvalid, float (&c0a)[4], float (&c0b)[4],
+__device__ __forceinline__ void tc_contract(unsigned frag, unsigned frag_b, int nvalid, float (&c0a)[4], float (&c0b)[4],
                                             float (&c1a)[4], float (&c1b)[4]);
 
 // ---------------------------------------------------------------------------------------------
@@ -455,6 +474,24 @@ __device__ __forceinline__ void cp_async16_if(bool on, unsigned dst, const void*
 }
 
 __device__ __forceinline__ void tc_store_rows(unsigned row_u, const float4 (&ur)[4], const float4 (&vr)[4]) {
+  if (kSwLdsm) {
+    // a row per residual in natural column order: ur / vr hold [c0 c8 | c1 c9], [c2 c10 | c3 c11], ... (tc_fp32_rows)
+    uint4 lo, hi;
+    lo.x = pack_f16x2(ur[0].x, ur[0].z); lo.y = pack_f16x2(ur[1].x, ur[1].z);
+    lo.z = pack_f16x2(ur[2].x, ur[2].z); lo.w = pack_f16x2(ur[3].x, ur[3].z);
+    hi.x = pack_f16x2(ur[0].y, ur[0].w); hi.y = pack_f16x2(ur[1].y, ur[1].w);
+    hi.z = pack_f16x2(ur[2].y, ur[2].w); hi.w = pack_f16x2(ur[3].y, ur[3].w);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_u), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_u + 16), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+    lo.x = pack_f16x2(vr[0].x, vr[0].z); lo.y = pack_f16x2(vr[1].x, vr[1].z);
+    lo.z = pack_f16x2(vr[2].x, vr[2].z); lo.w = pack_f16x2(vr[3].x, vr[3].z);
+    hi.x = pack_f16x2(vr[0].y, vr[0].w); hi.y = pack_f16x2(vr[1].y, vr[1].w);
+    hi.z = pack_f16x2(vr[2].y, vr[2].w); hi.w = pack_f16x2(vr[3].y, vr[3].w);
+    const unsigned row_v = row_u + 32 * kTcRow * 4;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_v), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_v + 16), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+    return;
+  }
   if (kSwF16) {
     // one row per observation: word p = (u row, v row) at tile position p, as FP16
 #pragma unroll
@@ -476,12 +513,38 @@ __device__ __forceinline__ void tc_store_rows(unsigned row_u, const float4 (&ur)
   }
 }
 
+__device__ __forceinline__ void ldsm_x4_trans(unsigned addr, unsigned& r0, unsigned& r1, unsigned& r2, unsigned& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr)
+               : "memory");
+}
+
 template <bool FULL>
-__device__ __forceinline__ void tc_contract(unsigned frag, int nvalid, float (&c0a)[4], float (&c0b)[4],
+__device__ __forceinline__ void tc_contract(unsigned frag, unsigned frag_b, int nvalid, float (&c0a)[4], float (&c0b)[4],
                                             float (&c1a)[4], float (&c1b)[4]) {
 #ifdef CCG_SW_NO_MMA  // timing experiment: no contraction (results are then wrong)
   return;
 #endif
+  if (kSwLdsm) {
+    // k-step s contracts observations 8s..8s+7: k = 0..7 -> their u rows, k = 8..15 -> their v rows
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (FULL || 8 * s < nvalid) {
+        unsigned a0, a1, a2, a3, b0, b1, b2, b3;
+        ldsm_x4_trans(frag + (8 * s) * kTcRow * 4, a0, a1, a2, a3);    // A = J' (16 parameters x 16 residual rows)
+        ldsm_x4_trans(frag_b + (8 * s) * kTcRow * 4, b0, b1, b2, b3);  // B: columns 0..7 (b0, b1), columns 8..15 (b2, b3)
+        if (s & 1) {
+          mma_f16_16x8x16(c0b, a0, a1, a2, a3, b0, b1);
+          mma_f16_16x8x16(c1b, a0, a1, a2, a3, b2, b3);
+        } else {
+          mma_f16_16x8x16(c0a, a0, a1, a2, a3, b0, b1);
+          mma_f16_16x8x16(c1a, a0, a1, a2, a3, b2, b3);
+        }
+      }
+    }
+    return;
+  }
   if (kSwF16) {
     // k-step s contracts observations 8s..8s+7: k = 2 tig, 2 tig + 1 -> (u, v) of observation 8s + 2 tig,
     // k = 2 tig + 8, + 9 -> the next observation; a fragment register is one tile word
@@ -608,10 +671,11 @@ __device__ __forceinline__ T* opaque_ptr(T* p) {
 // as the candidate pose and as the rotation matrix + translation the roles consume (double and float);
 // s_step[0..1] receive the item's share of the model terms g'd and d'Dd (fixed-order sums).
 // ---------------------------------------------------------------------------------------------
+template <int PAIRS>
 __device__ __forceinline__ void sw_candidate_poses(const IntrDev& d, const WorkItem& it, int par, const double* s_du,
-                                                   double (*s_red)[kSwWarps], double* s_step) {
+                                                   double (*s_red)[2 * PAIRS], double* s_step) {
   double gTd = 0.0, dDd = 0.0;
-  for (int64_t v = it.v0 + threadIdx.x; v < it.v1; v += kSwThreads) {
+  for (int64_t v = it.v0 + threadIdx.x; v < it.v1; v += 64 * PAIRS) {
     const double* yz = d.yz + (size_t)v * kYz;
     double dl[6];
 #pragma unroll
@@ -658,7 +722,7 @@ __device__ __forceinline__ void sw_candidate_poses(const IntrDev& d, const WorkI
   if (threadIdx.x < 2) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kSwWarps; ++w) s += s_red[threadIdx.x][w];
+    for (int w = 0; w < 2 * PAIRS; ++w) s += s_red[threadIdx.x][w];
     s_step[threadIdx.x] = s;
   }
 }
@@ -862,7 +926,12 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAhea
     usp[i] = (unsigned)opaque((int)usp[i]);
   }
   const unsigned row_u = tile + (unsigned)lane * (kTcRow * 4);            // this lane's u row (v row: + 32 rows)
-  const unsigned frag = tile + (unsigned)(2 * tig * kTcRow + 2 * g) * 4;  // this lane's fragment of k-step 0
+  // this lane's fragment of k-step 0 (LDS.64 layout) | its row address for the two ldmatrix of k-step 0: lanes 8i..8i+7
+  // address block i; A order: (u rows, columns 0..7), (u, 8..15), (v, 0..7), (v, 8..15); B order: (u, 0..7), (v, 0..7),
+  // (u, 8..15), (v, 8..15)
+  const unsigned frag = kSwLdsm ? tile + (unsigned)(((lane & 7) + 32 * ((lane >> 4) & 1)) * kTcRow * 4 + ((lane >> 3) & 1) * 16)
+                                : tile + (unsigned)(2 * tig * kTcRow + 2 * g) * 4;
+  const unsigned frag_b = (unsigned)opaque((int)(tile + (unsigned)(((lane & 7) + 32 * ((lane >> 3) & 1)) * kTcRow * 4 + ((lane >> 4) & 1) * 16)));
   float4 pn[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) pn[i] = rtf[(size_t)va * 3 + i];
@@ -896,22 +965,22 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAhea
       o0 = load();  // queue now: o1 next, o0 after it
       for (c -= 1; c >= 2; c -= 2) {
         tc_fp32_rows<false>(K, Rf, tf, o1.X, o1.Y, o1.Z, true, ur, vr);
-        tc_contract<true>(frag + t0, 32, c0a, c0b, c1a, c1b);
+        tc_contract<true>(frag + t0, frag_b + t0, 32, c0a, c0b, c1a, c1b);
         tc_store_rows(row_u + t1, ur, vr);
         o1 = load();
         tc_fp32_rows<false>(K, Rf, tf, o0.X, o0.Y, o0.Z, true, ur, vr);
-        tc_contract<true>(frag + t1, 32, c0a, c0b, c1a, c1b);
+        tc_contract<true>(frag + t1, frag_b + t1, 32, c0a, c0b, c1a, c1b);
         tc_store_rows(row_u + t0, ur, vr);
         o0 = load();
       }
       if (c == 1) {
         tc_fp32_rows<false>(K, Rf, tf, o1.X, o1.Y, o1.Z, true, ur, vr);
-        tc_contract<true>(frag + t0, 32, c0a, c0b, c1a, c1b);
+        tc_contract<true>(frag + t0, frag_b + t0, 32, c0a, c0b, c1a, c1b);
         tc_store_rows(row_u + t1, ur, vr);
         o1 = load();  // queue back in order: o0 next, o1 after it
-        tc_contract<true>(frag + t1, 32, c0a, c0b, c1a, c1b);
+        tc_contract<true>(frag + t1, frag_b + t1, 32, c0a, c0b, c1a, c1b);
       } else {
-        tc_contract<true>(frag + t0, 32, c0a, c0b, c1a, c1b);
+        tc_contract<true>(frag + t0, frag_b + t0, 32, c0a, c0b, c1a, c1b);
         const SwObs3 x = o0;
         o0 = o1;
         o1 = x;
@@ -929,8 +998,8 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAhea
         tc_fp32_rows<false>(K, Rf, tf, b.X, b.Y, b.Z, true, ur, vr);
         tc_store_rows(row_u + kTcTile * 4, ur, vr);
         __syncwarp();
-        tc_contract<true>(frag, 32, c0a, c0b, c1a, c1b);
-        tc_contract<true>(frag + kTcTile * 4, 32, c0a, c0b, c1a, c1b);
+        tc_contract<true>(frag, frag_b, 32, c0a, c0b, c1a, c1b);
+        tc_contract<true>(frag + kTcTile * 4, frag_b + kTcTile * 4, 32, c0a, c0b, c1a, c1b);
       }
     }
     for (; c >= 1; --c) {
@@ -941,7 +1010,7 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAhea
       tc_fp32_rows<false>(K, Rf, tf, a.X, a.Y, a.Z, true, ur, vr);
       tc_store_rows(row_u, ur, vr);
       __syncwarp();
-      tc_contract<true>(frag, 32, c0a, c0b, c1a, c1b);
+      tc_contract<true>(frag, frag_b, 32, c0a, c0b, c1a, c1b);
     }
     if (n & 31) {
       const SwObs3 a = o0;
@@ -951,7 +1020,7 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAhea
       tc_fp32_rows<true>(K, Rf, tf, a.X, a.Y, a.Z, lane < (n & 31), ur, vr);
       tc_store_rows(row_u, ur, vr);
       __syncwarp();
-      tc_contract<false>(frag, n & 31, c0a, c0b, c1a, c1b);
+      tc_contract<false>(frag, frag_b, n & 31, c0a, c0b, c1a, c1b);
     }
     // per-view epilogue: V, W blocks and the view's contribution to U
     double* blk = blk0 + (size_t)v * kBlk;
@@ -973,6 +1042,7 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAhea
 // roles, then the item's 64-value partial into `out` (global or shared memory).  s_k: intrinsics at the
 // candidate point, s_du: the reduced step (both in shared memory).
 // ---------------------------------------------------------------------------------------------
+template <int PAIRS>
 struct SwSmem {  // dynamic shared memory of a sweep CTA
   int* pace;  // per pair: blocks the FP64 warp has consumed (the Jacobian warp's pacing)
   double (*part)[kSweepPart];
@@ -981,19 +1051,20 @@ struct SwSmem {  // dynamic shared memory of a sweep CTA
     pace = reinterpret_cast<int*>(dyn);
     dyn += sizeof(int) * 16;
     part = reinterpret_cast<double(*)[kSweepPart]>(dyn);
-    stage_d = reinterpret_cast<float*>(dyn + sizeof(double) * kSwWarps * kSweepPart);
-    stage_j = stage_d + kSwPairs * kSwStagesD * kSwStageD;
-    tiles = stage_j + kSwPairs * kSwStagesJ * kSwStageJ;
+    stage_d = reinterpret_cast<float*>(dyn + sizeof(double) * 2 * PAIRS * kSweepPart);
+    stage_j = stage_d + PAIRS * kSwStagesD * kSwStageD;
+    tiles = stage_j + PAIRS * kSwStagesJ * kSwStageJ;
   }
 };
 
 // ROLE: 0 = the calling CTA's warps take their roles here and split the registers (the sweep as a launch of
 // its own); 1 / 2 = the caller is an FP64 / a Jacobian warp whose registers are already set (the persistent LM
 // kernel instantiates its whole loop once per role, so that no code is shared between the two register budgets).
-template <bool RES, int ROLE>
+template <bool RES, int ROLE, int PAIRS>
 __device__ __forceinline__ void sw_sweep_item(const IntrDev& d, const WorkItem& it, int par, const double* s_k,
-                                              const double* s_du, const SwSmem& sm, double (*s_red)[kSwWarps],
+                                              const double* s_du, const SwSmem<PAIRS>& sm, double (*s_red)[2 * PAIRS],
                                               double* s_step, double* out, double* __restrict__ res_out) {
+  constexpr int kSwPairs = PAIRS, kSwWarps = 2 * PAIRS, kSwThreads = 64 * PAIRS;  // (shadow the 8-pair constants)
   for (int i = threadIdx.x; i < kSwWarps * kSweepPart; i += kSwThreads) (&sm.part[0][0])[i] = 0.0;
   if (threadIdx.x < kSwPairs) sm.pace[threadIdx.x] = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1018,7 +1089,7 @@ __device__ __forceinline__ void sw_sweep_item(const IntrDev& d, const WorkItem& 
     if (is_d) strm_d.init(d.obs_blk, d.vmeta[va].x, d.vmeta[vsplit].x, smem_u32(sm.stage_d + pair * kSwStagesD * kSwStageD), lane);
     else strm_j.init(d.obs_blk, d.vmeta[va].x, d.vmeta[vb].x, smem_u32(sm.stage_j + pair * kSwStagesJ * kSwStageJ), lane);
   }
-  sw_candidate_poses(d, it, par, s_du, s_red, s_step);  // (its barrier also covers the zeroing above)
+  sw_candidate_poses<PAIRS>(d, it, par, s_du, s_red, s_step);  // (its barrier also covers the zeroing above)
   if (!kEarly) {
     if (is_d) strm_d.init(d.obs_blk, d.vmeta[va].x, d.vmeta[vsplit].x, smem_u32(sm.stage_d + pair * kSwStagesD * kSwStageD), lane);
     else strm_j.init(d.obs_blk, d.vmeta[va].x, d.vmeta[vb].x, smem_u32(sm.stage_j + pair * kSwStagesJ * kSwStageJ), lane);
@@ -1065,11 +1136,11 @@ __device__ __forceinline__ void sw_sweep_item(const IntrDev& d, const WorkItem& 
 }
 
 // The sweep as a launch of its own: one CTA per work item, state read from global memory.
-template <bool RES>
-__global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, double* __restrict__ res_out) {
+template <bool RES, int PAIRS>
+__global__ void __launch_bounds__(64 * PAIRS, 8 / PAIRS) k_intr_sweep_ws(IntrDev d, double* __restrict__ res_out) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ double s_k[9], s_du[9], s_step[2];
-  __shared__ double s_red[2][kSwWarps];
+  __shared__ double s_red[2][2 * PAIRS];
   __shared__ int s_meta[2];
   const WorkItem it = d.items[blockIdx.x];
   IntrState& ps = d.ps[it.problem];
@@ -1085,8 +1156,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_intr_sweep_ws(IntrDev d, doub
     s_du[threadIdx.x] = ps.du[threadIdx.x];
   }
   __syncthreads();
-  sw_sweep_item<RES, 0>(d, it, par, s_k, s_du, SwSmem(s_dyn), s_red, s_step,
-                            d.sweep_part + (size_t)blockIdx.x * kSweepPart, res_out);
+  sw_sweep_item<RES, 0, PAIRS>(d, it, par, s_k, s_du, SwSmem<PAIRS>(s_dyn), s_red, s_step,
+                               d.sweep_part + (size_t)blockIdx.x * kSweepPart, res_out);
 }
 
 // Observations SoA -> 640-byte blocks of 32 (views padded to whole blocks with zeros); one warp per view.

@@ -809,12 +809,17 @@ __device__ __forceinline__ void rig_state_out(RigState* g, const RigState& sh) {
 // FUSED: the kernel also reduces the per-item sweep partials itself (one launch instead of k_rig_reduce + k_rig_decide;
 // a problem that is not partitioned over GPUs needs nothing in between).  1024 threads: thread (c, seg) sums items
 // seg, seg + 8, ... of component c, the 8 segment sums are combined in order - only the 27 C + 5 components in use.
+// peer != 0 (frames partitioned over GPUs, FUSED only): the reduced partial is all-reduced over peer memory inside this
+// launch (peer_allreduce_n, common.cuh) - every rank holds the same LM state, so all of them are here - instead of
+// k_rig_reduce + ncclAllReduce + k_rig_decide<false>.
 template <bool FUSED>
-__global__ void __launch_bounds__(FUSED ? 1024 : 256) k_rig_decide(RigDev d, LmParams P, int n_items) {
+__global__ void __launch_bounds__(FUSED ? 1024 : 256) k_rig_decide(RigDev d, LmParams P, int n_items, PeerComm pc, int peer) {
   __shared__ double s_buf[kRigPart];
   __shared__ double s_seg[8][128];
   __shared__ RigState ps;
+  __shared__ int s_comm_ok;
   if (d.ps[0].lm.status != 0) return;
+  if (threadIdx.x == 0) s_comm_ok = 1;
   rig_state_in(ps, d.ps);
   const bool evaluated = ps.lm.solve_ok != 0;
   if (evaluated && FUSED) {
@@ -839,6 +844,10 @@ __global__ void __launch_bounds__(FUSED ? 1024 : 256) k_rig_decide(RigDev d, LmP
       }
       __syncthreads();
     }
+    if (peer) {
+      const bool ok = peer_allreduce_n(s_buf, kRigPart, pc);
+      if (threadIdx.x == 0) s_comm_ok = ok ? 1 : 0;
+    }
   } else if (evaluated) {
     for (int c = threadIdx.x; c < kRigPart; c += blockDim.x) s_buf[c] = d.red_sweep[c];
     __syncthreads();
@@ -849,6 +858,8 @@ __global__ void __launch_bounds__(FUSED ? 1024 : 256) k_rig_decide(RigDev d, LmP
       lm_reject(s, P, d.n_done);
       s.solve_ok = 1;
       if (s.status == 0 && s.iterations >= P.max_iterations) lm_finish(s, 4, d.n_done, true);
+    } else if (!s_comm_ok) {  // the peer-memory allreduce timed out
+      lm_finish(s, CCG_ERR_NCCL, d.n_done, false);
     } else {
       const double* r = s_buf;
       const int base = 27 * kMaxCams;
@@ -1073,13 +1084,22 @@ __device__ __forceinline__ void rig_solve_body(const RigDev& d, const LmParams& 
   rig_apply_step(ps, s, rhs, Du, C, par);
 }
 
-__global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P) {
+// peer != 0: the rank's reduced system in d.red_schur is first all-reduced over peer memory, in place.
+__global__ void __launch_bounds__(256) k_rig_solve(RigDev d, LmParams P, PeerComm pc, int peer) {
   extern __shared__ double s_dyn[];
   __shared__ int s_flag[2];
   __shared__ double s_piv;
   __shared__ RigState ps;
   if (!(d.ps[0].lm.status == 0 || d.ps[0].lm.finalize)) return;
   rig_state_in(ps, d.ps);
+  if (peer && !peer_allreduce_n(d.red_schur, d.schur_stride, pc)) {  // (uniform over the CTA)
+    if (threadIdx.x == 0) {
+      ps.lm.finalize = 0;
+      if (ps.lm.status == 0) lm_finish(ps.lm, CCG_ERR_NCCL, d.n_done, false);
+    }
+    rig_state_out(d.ps, ps);
+    return;
+  }
   rig_solve_body(d, P, ps, s_dyn, s_flag, s_piv);  // (threads leave the body at different points; they meet again here)
   rig_state_out(d.ps, ps);
 }
@@ -1314,15 +1334,19 @@ int rig_sweep_decide(ccg_rig_problem* p, const LmParams& P, Profiler& prof, doub
   prof.end();
   ctx->launches++;
   prof.begin(TAG_SMALL);
-  if (p->shared && ctx->world > 1) {
+  const PeerComm pc = peer_comm(ctx);
+  if (p->shared && ctx->world > 1 && !ctx->peer_ok) {
     k_rig_reduce<<<(kRigPart + 31) / 32, 32 * kRigRedSeg, 0, st>>>(d.sweep_part, kRigPart, p->n_items, d.red_sweep);
     CCG_TRY(nccl_allreduce_sum(ctx, d.red_sweep, kRigPart));
     (*nar)++;
-    k_rig_decide<false><<<1, 256, 0, st>>>(d, P, p->n_items);
+    k_rig_decide<false><<<1, 256, 0, st>>>(d, P, p->n_items, pc, 0);
     ctx->launches += 2;
   } else {
-    k_rig_decide<true><<<1, 1024, 0, st>>>(d, P, p->n_items);
+    // frames partitioned over GPUs: the allreduce runs over peer memory inside the launch
+    const int peer = (p->shared && ctx->world > 1) ? 1 : 0;
+    k_rig_decide<true><<<1, 1024, 0, st>>>(d, P, p->n_items, pc, peer);
     ctx->launches++;
+    *nar += peer;
   }
   prof.end();
   return CCG_OK;
@@ -1338,11 +1362,13 @@ int rig_schur_solve(ccg_rig_problem* p, const LmParams& P, Profiler& prof, int* 
   ctx->launches++;
   prof.begin(TAG_SMALL);
   k_rig_reduce<<<(d.schur_stride + 31) / 32, 32 * kRigRedSeg, 0, st>>>(d.schur_part, d.schur_stride, p->n_items, d.red_schur);
+  int peer = 0;
   if (p->shared && ctx->world > 1) {
-    CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, (size_t)d.schur_stride));
+    if (ctx->peer_ok) peer = 1;  // all-reduced over peer memory inside k_rig_solve
+    else CCG_TRY(nccl_allreduce_sum(ctx, d.red_schur, (size_t)d.schur_stride));
     (*nar)++;
   }
-  k_rig_solve<<<1, 256, p->solve_smem, st>>>(d, P);
+  k_rig_solve<<<1, 256, p->solve_smem, st>>>(d, P, peer_comm(ctx), peer);
   ctx->launches += 2;
   prof.end();
   return CCG_OK;
@@ -1362,6 +1388,12 @@ int rig_run(ccg_rig_problem* p, const ccg_opts& opts, ccg_timing* timing) {
   int nar = 0;
   cudaEventRecord(ctx->events[e0], ctx->stream);
   CCG_TRY(rig_reset(p, P));
+  if (p->shared && ctx->world > 1 && ctx->peer_ok) {
+    // line the ranks up once per solve with a collective that waits without a deadline (the peer-memory allreduces
+    // inside the kernels then only see the skew of one LM iteration) and agree on their sequence number
+    CCG_TRY(peer_resync(ctx, p->dev.red_sweep));
+    nar++;
+  }
   CCG_TRY(rig_sweep_decide(p, P, prof, nullptr, &nar));
   // one LM iteration (six launches, allreduces included) replayed as a CUDA graph when no
   // per-kernel events are requested and the problem object is reused (CCG_NO_GRAPH=1 disables)
