@@ -120,9 +120,10 @@ constexpr int kTcTile = ((kSwF16 && !kSwLdsm) ? 32 : 64) * kTcRow;  // one 32-ob
 
 // The Jacobian warp of a pair is the faster one; left alone it runs ahead of its FP64 partner by more than L2 holds
 // (all pairs of the GPU together), and every block is then fetched from HBM twice (measured: 1.70 x the algorithmic
-// bytes).  It therefore never requests a block more than kSwLead blocks beyond the one its partner has consumed.
+// bytes).  Paced, it starts a view only while it is within kSwLead blocks of what its partner has finished (checked
+// once per view; the partner publishes its block count once per view).  0 = unpaced.
 #ifndef CCG_SW_LEAD
-#define CCG_SW_LEAD 0
+#define CCG_SW_LEAD 64
 #endif
 constexpr int kSwLead = CCG_SW_LEAD;
 constexpr size_t sw_smem_bytes(int pairs) {
@@ -761,10 +762,6 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, SwStream<5, kSwAhe
     int consumed = 0;  // blocks read so far, published for the partner's pacing
     auto load = [&]() -> SwObs5 {
       const unsigned a = strm.next(lane);
-      if (!LEAN && kSwLead > 0) {  // (published only when the partner is paced)
-        ++consumed;
-        if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(pace), "r"(consumed) : "memory");
-      }
       SwObs5 o;
       o.mu = lds_f32(a); o.mv = lds_f32(a + 128); o.X = lds_f32(a + 256); o.Y = lds_f32(a + 384); o.Z = lds_f32(a + 512);
       return o;
@@ -849,6 +846,10 @@ __device__ __forceinline__ void sw_run_fp64(const IntrDev& d, SwStream<5, kSwAhe
       if (lane == 1) out = 2.0 * (r - (t[2] * sw0 - t[0] * sw2));
       if (lane == 2) out = 2.0 * (r - (t[0] * sw1 - t[1] * sw0));
       if (lane < 6) gv_out[(size_t)v * kBlk] = out;
+      if (!LEAN && kSwLead > 0) {  // blocks consumed so far, published once per view (only when the partner is paced)
+        consumed += (n + 31) >> 5;
+        if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(pace), "r"(consumed) : "memory");
+      }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
@@ -890,20 +891,8 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAhea
   const int2* vmeta = opaque_ptr(d.vmeta);
   const float4* rtf = reinterpret_cast<const float4*>(opaque_ptr(d.rtf));
   double* blk0 = opaque_ptr(d.blk[par ^ 1]);
-  int requested = 0;
+  int started = 0;  // blocks of the views this warp has started (pacing)
   auto load = [&]() -> SwObs3 {
-    // pacing: stay within kSwLead blocks of the FP64 partner (see kSwLead)
-    ++requested;
-#ifndef CCG_SW_ONLY_J
-    if (kSwLead > 0 && kSwTail == 0) {
-      for (;;) {
-        int seen;
-        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(seen) : "r"(pace) : "memory");
-        if (requested - kSwLead <= seen) break;  // (seen = INT_MAX once the partner is done)
-        __nanosleep(256);
-      }
-    }
-#endif
     const unsigned a = strm.next(lane);
     SwObs3 o;
     o.X = lds_f32(a); o.Y = lds_f32(a + 128); o.Z = lds_f32(a + 256);
@@ -946,6 +935,18 @@ __device__ __forceinline__ void sw_run_jac(const IntrDev& d, SwStream<3, kSwAhea
       for (int i = 0; i < 3; ++i) pn[i] = rtf[(size_t)vn * 3 + i];
       n_next = vmeta[vn].y;
     }
+#ifndef CCG_SW_ONLY_J
+    if (kSwLead > 0 && kSwTail == 0) {
+      // pacing, once per view: start a view only within kSwLead blocks of what the FP64 partner has finished (see kSwLead)
+      for (;;) {
+        int seen;
+        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(seen) : "r"(pace) : "memory");
+        if (started - kSwLead <= seen) break;  // (seen = INT_MAX once the partner is done)
+        __nanosleep(128);
+      }
+      started += (n + 31) >> 5;
+    }
+#endif
     // product columns 0..7 (c0*) and 8..15 (c1*), two accumulator sets each
     float c0a[4] = {0.f, 0.f, 0.f, 0.f}, c0b[4] = {0.f, 0.f, 0.f, 0.f};
     float c1a[4] = {0.f, 0.f, 0.f, 0.f}, c1b[4] = {0.f, 0.f, 0.f, 0.f};

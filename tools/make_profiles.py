@@ -71,7 +71,7 @@ sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active sm__pipe_shared_cycl
 l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed l1tex__data_pipe_lsu_wavefronts_mem_shared.sum
 l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum
 l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum""".split()
-    out = [f"# ncu --set full: `k_intr_sweep_ws<0>` at FULL C5 size (100,000 views x 400 points, one launch = 4e7 observations), round {rnd}", "",
+    out = [f"# ncu --set full: `k_intr_sweep_ws<0, 8>` at FULL C5 size (100,000 views x 400 points, one launch = 4e7 observations), round {rnd}", "",
            f"Capture: `ncu --set full --clock-control none --import-source on -k regex:k_intr_sweep -s 2 -c 1 python tools/profile_sweep.py 100000 400` "
            f"(`tools/gpu_evidence.sh`), after the same command had exited 0 without ncu.  The .ncu-rep stays in gpurun_out/ (scratch).", "",
            "| metric | value | unit |", "|---|---|---|"]
@@ -94,7 +94,7 @@ l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum""".split()
         return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
 
     traffic = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-    json.dump({"_note": f"dram__bytes_read.sum + dram__bytes_write.sum of k_intr_sweep_ws<0> from the full-size ncu --set full capture "
+    json.dump({"_note": f"dram__bytes_read.sum + dram__bytes_write.sum of k_intr_sweep_ws<0, 8> from the full-size ncu --set full capture "
                         f"{rnd}_sweep_ncu_full.md (100,000 views x 400 points, one launch); read by bench.py for roofline.traffic",
                "c5": {"sweep_dram_bytes_per_launch": int(traffic), "dram_read": int(num("dram__bytes_read.sum")),
                       "dram_write": int(num("dram__bytes_write.sum"))}}, open(f"{P}/traffic.json", "w"), indent=1)
