@@ -7,35 +7,39 @@
 // per view  [V W; W' U] = sum over its 2P residual rows of (row)'(row), a 16 x 16 x 2P product.
 //   FP64 pipe  : forward model, residual, cost, and g_v / g_u by REVERSE mode (no explicit J)
 //   FP32 pipe  : a second forward pass and the analytic 2 x 15 Jacobian rows
-//   tensor pipe: J'J by mma.sync.m16n8k8 TF32 with FP32 accumulation - one lane owns one
-//                observation, writes its two Jacobian rows to a warp-private shared-memory tile,
-//                and the warp contracts 32 observations with 16 MMAs; the A fragment doubles as
-//                the B fragment (the product is J'J), so a k-step costs two LDS.64.
+//   tensor pipe: J'J by mma.sync.m16n8k16 with FP16 operands and FP32 accumulation - one lane owns one
+//                observation, writes its two Jacobian rows (FP16) to a warp-private shared-memory tile,
+//                and the warp contracts 32 observations with 8 MMAs; the B fragments are the A
+//                fragment's registers regrouped (the product is J'J), and two ldmatrix.x4.trans per
+//                k-step deliver both groupings without register moves.
 //
-// Roles (one CTA per SM, one work item = a range of views per CTA):
-//   * the CTA runs kSwPairs warp PAIRS, two per SM sub-partition: an FP64-role warp (the higher warp
-//     ids: the issue arbiter prefers them) and a Jacobian-role warp that walk the SAME contiguous
-//     range of views, each on its own - they share nothing but the read-only inputs, so there is no
-//     synchronisation inside the loops, and the second reader of an observation block hits L1/L2
-//     (HBM traffic stays 20 B per observation).  setmaxnreg gives the FP64 warps kSwRegD registers
-//     and leaves the Jacobian warps kSwRegJ.
+// Roles (one work item = a range of views per CTA; template parameter PAIRS = warp pairs per CTA):
+//   * an SM runs 8 warp PAIRS, two per SM sub-partition, as one CTA of 8 or two CTAs of 4: an FP64-role
+//     warp (the higher warp ids) and a Jacobian-role warp that walk the SAME contiguous range of views,
+//     each on its own - they share nothing but the read-only inputs, so there is no synchronisation inside
+//     the loops; once per view the Jacobian warp checks that it is not too far ahead of its partner
+//     (kSwLead), so that the second reader of an observation block hits L2 (HBM traffic 1.19 x the 20 B
+//     per observation).  setmaxnreg gives the FP64 warps kSwRegD registers and leaves the Jacobian
+//     warps kSwRegJ.
 //
 // Observation stream: the observations live in HBM as 640-byte blocks of 32 observations
 // (u[32] v[32] X[32] Y[32] Z[32], views padded to whole blocks with zeros), so a 32-observation
 // chunk is ONE aligned block and the blocks of a warp's view range are one contiguous stream:
 // two 16-byte cp.async per lane (one for the Jacobian role, which reads X Y Z only) fetch block
 // k + kSwAhead* into a small per-warp ring while block k is consumed - no view logic on that path.
-// A warp loads the NEXT chunk's observation into registers before it computes the current one
+// A warp loads the NEXT chunks' observations into registers before it computes the current one
 // (shared-memory latency off the dependent chain).  Loops: views outside (pose and size of the next
 // view are fetched one view ahead with plain loads), full chunks inside, the partial last chunk of
 // a view peeled off, so the inner loops carry no masking and no view bookkeeping.
 //
-// Operand precision: the raw float32 rows are fed to the TF32 unit (10 explicit mantissa bits).
+// Operand precision: the float32 rows are rounded to FP16 (11 significant bits, as TF32; the pose columns
+// are scaled by a power of two so that nothing leaves the FP16 range, and the conversion saturates).
 // tools/h_precision_study.py shows that the exact-Schur LM takes the same iterations with such
-// blocks and lands within 1e-10 of the all-FP64 solve (oracle experiment mode 311).
+// blocks and lands within 1e-10 of the all-FP64 solve (oracle experiment mode 311); CCG_SW_F16=0 keeps the
+// TF32 m16n8k8 variant.
 // Why legacy mma.sync and not tcgen05: the tile is 16 x 16 per VIEW; tcgen05's smallest M is 64,
 // so four views would share an instruction through a block-diagonal A with 3/4 zeros, which makes
-// it slower per observation than mma.sync (measured 8.6 cycles per m16n8k8 per SM sub-partition,
+// it slower per observation than mma.sync (measured 8.6 cycles per mma.sync per SM sub-partition,
 // tools/ubench_pipes.cu) while the kernel is bound by instruction issue, not by the tensor pipe.
 #pragma once
 
