@@ -76,3 +76,39 @@ def test_allreduced_partial_systems_equal_the_full_system(tmp_path):
     err = np.load(tmp_path / "err.npy")
     assert err.max() <= 1e-12
     assert np.load(tmp_path / "blk.npy")[0] == 0.0
+
+
+def _rig_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from camera_calibrator_b200 import partition as part
+    from camera_calibrator_b200 import synth
+
+    # the rig is partitioned by FRAME: camera extrinsics replicated, every rank contributes the
+    # camera blocks U_cc, the camera gradient and the robust cost of its frames (what k_rig_decide all-reduces)
+    s = synth.rig_scene(n_cams=3, n_frames=9, grid=(5, 4), seed=4, outlier_fraction=0.1)
+    huber = float(np.float32(3.0) / np.float32(500.0))
+    fa, fb = part.split_range(9, world, rank)
+    o0, o1 = int(s.frame_offsets[fa]), int(s.frame_offsets[fb])
+    e = oracle.rig_eval(s.u[o0:o1], s.v[o0:o1], s.obs_cam[o0:o1], s.obs_point[o0:o1], s.frame_offsets[fa:fb + 1] - o0,
+                        s.Xw, s.q_c, s.t_c, s.q_f[fa:fb], s.t_f[fa:fb], huber)
+    buf = torch.tensor(np.concatenate([e["U"].ravel(), e["gu"], [e["cost"]], [float(o1 - o0)]]))
+    dist.all_reduce(buf)
+    if rank == 0:
+        full = oracle.rig_eval(s.u, s.v, s.obs_cam, s.obs_point, s.frame_offsets, s.Xw, s.q_c, s.t_c, s.q_f, s.t_f, huber)
+        ref = np.concatenate([full["U"].ravel(), full["gu"], [full["cost"]], [float(s.frame_offsets[-1])]])
+        scale = np.maximum(np.abs(ref), 1e-300)
+        np.save(os.path.join(out_dir, "rig_err.npy"), np.abs(buf.numpy() - ref) / np.maximum(scale, np.abs(ref).max() * 1e-12))
+        # per-frame blocks are rank-local: exactly the corresponding slice of the full evaluation
+        np.save(os.path.join(out_dir, "rig_blk.npy"),
+                np.array([np.max(np.abs(e["V"] - full["V"][fa:fb])), np.max(np.abs(e["W"] - full["W"][fa:fb]))]))
+    dist.destroy_process_group()
+
+
+def test_allreduced_partial_rig_systems_equal_the_full_system(tmp_path):
+    port = _free_port()
+    mp.spawn(_rig_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert np.load(tmp_path / "rig_err.npy").max() <= 1e-12
+    assert np.all(np.load(tmp_path / "rig_blk.npy") == 0.0)
