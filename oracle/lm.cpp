@@ -67,6 +67,12 @@ static void chol_solve(const double* L, int n, double* b) {
 static inline double clampd(double x, double lo, double hi) { return std::min(std::max(x, lo), hi); }
 
 static int g_h_float = 0;  // experiment switch, see eval_single
+// EXPERIMENT switch for the gradient g = J'r of eval_single (tools/g_precision_study.py): 0 = double (the solver);
+// 1 = Jacobian entries rounded to float32, residual and sums in double; 2 = float32 Jacobian, float32 residual,
+// float32 sums flushed every 13 observations (a lane's share of a view); 3 = Jacobian and residual rounded to 11
+// significant bits (FP16 operands), float32 sums.  Answers: how far does the minimum move if a sweep kernel took the
+// gradient from its float32 Jacobian rows instead of an FP64 reverse pass?
+static int g_g_float = 0;
 
 // relative cost noise allowed when taking a final sub-resolution step
 static const double kNoise = 1e-12;
@@ -127,7 +133,33 @@ static void eval_single(const SingleData& D, const double* intr, const double* q
     double* guv = Uv + 81;
     double cost = 0.0;
     float Uf[81] = {0}, Vf[36] = {0}, Wf[54] = {0};
+    float guf[9] = {0}, gvf[6] = {0};
+    auto rnd11 = [](float x) {
+      if (x == 0.0f) return 0.0f;
+      int e;
+      const float m = std::ldexp(std::frexp(x, &e), 11);
+      return std::ldexp(std::nearbyint(m), e - 11);
+    };
+    // the gradient contribution of one residual row under the experiment switch g_g_float (guv / gvv += J' r)
+    auto add_gradient = [&](const double* Ji, const double* Jp, double rr) {
+      if (g_g_float == 0) {
+        for (int a = 0; a < 9; ++a) guv[a] += Ji[a] * rr;
+        for (int a = 0; a < 6; ++a) gvv[a] += Jp[a] * rr;
+      } else if (g_g_float == 1) {
+        for (int a = 0; a < 9; ++a) guv[a] += (double)(float)Ji[a] * rr;
+        for (int a = 0; a < 6; ++a) gvv[a] += (double)(float)Jp[a] * rr;
+      } else {
+        const float rf = g_g_float == 3 ? rnd11((float)rr) : (float)rr;
+        for (int a = 0; a < 9; ++a) guf[a] += (g_g_float == 3 ? rnd11((float)Ji[a]) : (float)Ji[a]) * rf;
+        for (int a = 0; a < 6; ++a) gvf[a] += (g_g_float == 3 ? rnd11((float)Jp[a]) : (float)Jp[a]) * rf;
+      }
+    };
+    auto flush_gradient = [&]() {
+      for (int a = 0; a < 9; ++a) { guv[a] += guf[a]; guf[a] = 0; }
+      for (int a = 0; a < 6; ++a) { gvv[a] += gvf[a]; gvf[a] = 0; }
+    };
     for (int64_t o = D.voff[iv]; o < D.voff[iv + 1]; ++o) {
+      if (g_g_float >= 2 && ((o - D.voff[iv]) % 13) == 12) flush_gradient();
       if (g_h_float && ((o - D.voff[iv]) % 13) == 12) {  // flush like a lane's ~13 observations
         for (int k = 0; k < 81; ++k) { Uv[k] += Uf[k]; Uf[k] = 0; }
         for (int k = 0; k < 36; ++k) { Vv[k] += Vf[k]; Vf[k] = 0; }
@@ -176,39 +208,37 @@ static void eval_single(const SingleData& D, const double* intr, const double* q
             for (int a = 0; a < 6; ++a) { hi[a] = rnd(Jpf[a]); lo[a] = two ? rnd(Jpf[a] - hi[a]) : 0.0f; }
             for (int a = 0; a < 9; ++a) { hi[6 + a] = rnd(Jif[a]); lo[6 + a] = two ? rnd(Jif[a] - hi[6 + a]) : 0.0f; }
             auto prod = [&](int a, int b) { return hi[a] * hi[b] + (hi[a] * lo[b] + lo[a] * hi[b]); };
+            add_gradient(Ji, Jp, rr);
             for (int a = 0; a < 9; ++a) {
-              guv[a] += Ji[a] * rr;
               for (int b = 0; b < 9; ++b) Uf[a * 9 + b] += prod(6 + a, 6 + b);
             }
             for (int a = 0; a < 6; ++a) {
-              gvv[a] += Jp[a] * rr;
               for (int b = 0; b < 6; ++b) Vf[a * 6 + b] += prod(a, b);
               for (int b = 0; b < 9; ++b) Wf[a * 9 + b] += prod(a, 6 + b);
             }
             continue;
           }
+          add_gradient(Ji, Jp, rr);
           for (int a = 0; a < 9; ++a) {
-            guv[a] += Ji[a] * rr;
             for (int b = 0; b < 9; ++b) Uf[a * 9 + b] += Jif[a] * Jif[b];
           }
           for (int a = 0; a < 6; ++a) {
-            gvv[a] += Jp[a] * rr;
             for (int b = 0; b < 6; ++b) Vf[a * 6 + b] += Jpf[a] * Jpf[b];
             for (int b = 0; b < 9; ++b) Wf[a * 9 + b] += Jpf[a] * Jif[b];
           }
           continue;
         }
+        add_gradient(Ji, Jp, rr);
         for (int a = 0; a < 9; ++a) {
-          guv[a] += Ji[a] * rr;
           for (int b = 0; b < 9; ++b) Uv[a * 9 + b] += Ji[a] * Ji[b];
         }
         for (int a = 0; a < 6; ++a) {
-          gvv[a] += Jp[a] * rr;
           for (int b = 0; b < 6; ++b) Vv[a * 6 + b] += Jp[a] * Jp[b];
           for (int b = 0; b < 9; ++b) Wv[a * 9 + b] += Jp[a] * Ji[b];
         }
       }
     }
+    if (g_g_float >= 2) flush_gradient();
     if (g_h_float) {
       for (int k = 0; k < 81; ++k) Uv[k] += Uf[k];
       for (int k = 0; k < 36; ++k) Vv[k] = (double)(float)(Vv[k] + Vf[k]);
@@ -783,6 +813,7 @@ using namespace oracle;
 extern "C" {
 
 void oracle_set_h_float(int on) { oracle::g_h_float = on; }
+void oracle_set_g_float(int mode) { oracle::g_g_float = mode; }
 
 void oracle_default_opts(oracle_opts* o) {
   o->max_iterations = 100;
