@@ -106,7 +106,10 @@ int ccg_device_info(ccg_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t*
  * the launcher (torch.distributed / file / env).  After ccg_comm_init, problems
  * created with shared=1 are treated as ONE calibration whose views (frames) are
  * partitioned across ranks: each LM iteration all-reduces the packed reduced
- * system over NCCL. */
+ * system - over peer memory (CUDA IPC mailboxes, NVLink) inside
+ * the accept/reject and reduced-solve kernels, for the single-camera and the
+ * rig solver; over ncclAllReduce when the mailboxes cannot be mapped or
+ * CCG_NO_PEER=1.  ccg_comm_init also exchanges the mailbox handles. */
 int ccg_comm_unique_id(uint8_t id_out[128]);
 int ccg_comm_init(ccg_ctx* ctx, int rank, int world_size, const uint8_t id[128]);
 int ccg_comm_barrier(ccg_ctx* ctx);
