@@ -285,3 +285,73 @@ def test_rig_oracle_matches_golden_fixture():
     assert np.max(np.abs(tf - np.array(sp["t_f"]))) <= 2e-5
     assert np.allclose(cost, np.array(sp["obs_cost"]), rtol=1e-3, atol=1e-9)
     assert abs(rep["final_cost"] - g["oracle"]["final_cost"]) <= 1e-12 * g["oracle"]["final_cost"]  # regression pin
+
+
+def test_rig_jacobian_blocks_match_torch_autograd():
+    """Rig oracle (two chained transforms, Ceres quaternion manifold, Huber corrector with
+    rho'' <= 0 = residual and Jacobian scaled by sqrt(rho')) vs torch.float64 autograd with the manifold perturbation
+    q <- exp_q(delta) * q applied explicitly to frame and camera poses: res, V_f, W_fc, g_f, U, g_c, cost."""
+    import torch
+
+    from camera_calibrator_b200 import synth
+
+    C_, F_, G = 3, 4, (3, 2)
+    P = G[0] * G[1]
+    s = synth.rig_scene(n_cams=C_, n_frames=F_, grid=G, seed=11, outlier_fraction=0.3, order="frame-major")
+    a = float(np.float32(3.0) / np.float32(500.0))
+    # evaluated at the TRUE poses: inliers sit below the Huber threshold, the 30 % gross outliers above it
+    e = oracle.rig_eval(s.u, s.v, s.obs_cam, s.obs_point, s.frame_offsets, s.Xw, s.q_c_true, s.t_c_true, s.q_f_true,
+                        s.t_f_true, a)
+    n = s.u.size
+    frame_of = np.repeat(np.arange(F_), np.diff(s.frame_offsets))
+    Xw = torch.tensor(s.Xw.astype(np.float64))[torch.tensor(s.obs_point)]
+    meas = torch.tensor(np.stack([s.u, s.v], 1).astype(np.float64))
+    qc0, tc0 = torch.tensor(s.q_c_true), torch.tensor(s.t_c_true)
+    qf0, tf0 = torch.tensor(s.q_f_true), torch.tensor(s.t_f_true)
+    cam = torch.tensor(s.obs_cam.astype(np.int64))
+    frm = torch.tensor(frame_of)
+
+    def plus(q, dl):
+        nrm = dl.norm(dim=-1, keepdim=True)
+        qd = torch.cat([torch.cos(nrm), torch.sinc(nrm / np.pi) * dl], -1)
+        w0, x0, y0, z0 = qd.unbind(-1)
+        w1, x1, y1, z1 = q.unbind(-1)
+        return torch.stack([w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1, w0 * x1 + x0 * w1 + y0 * z1 - z0 * y1,
+                            w0 * y1 - x0 * z1 + y0 * w1 + z0 * x1, w0 * z1 + x0 * y1 - y0 * x1 + z0 * w1], -1)
+
+    def rotate(q, x):  # ceres::QuaternionRotatePoint: normalises q
+        q = q / q.norm(dim=-1, keepdim=True)
+        w, v = q[..., :1], q[..., 1:]
+        t2 = 2.0 * torch.cross(v, x, dim=-1)
+        return x + w * t2 + torch.cross(v, t2, dim=-1)
+
+    def f(params):
+        df = params[:6 * F_].reshape(F_, 6)
+        dc = params[6 * F_:].reshape(C_, 6)
+        qf, tf = plus(qf0, df[:, :3]), tf0 + df[:, 3:]
+        qc, tc = plus(qc0, dc[:, :3]), tc0 + dc[:, 3:]
+        x_rig = rotate(qf[frm], Xw) + tf[frm]
+        x = rotate(qc[cam], x_rig) + tc[cam]
+        return (x[:, :2] / x[:, 2:3] - meas).reshape(-1)
+
+    p0 = torch.zeros(6 * (F_ + C_), dtype=torch.float64)
+    p0[:] = 1e-300  # (the norm in plus() is not differentiable at exactly 0)
+    J = torch.autograd.functional.jacobian(f, p0).numpy()
+    r = f(p0).detach().numpy().reshape(n, 2)
+    sq = np.sum(r * r, axis=1)
+    rho1 = np.where(sq <= a * a, 1.0, a / np.sqrt(np.maximum(sq, 1e-300)))
+    rho = np.where(sq <= a * a, sq, 2 * a * np.sqrt(sq) - a * a)
+    assert np.any(rho1 < 1.0) and np.any(rho1 == 1.0)  # both Huber zones are exercised
+    w = np.repeat(np.sqrt(rho1), 2)
+    Jw, rw = J * w[:, None], r.reshape(-1) * w
+    assert abs(0.5 * rho.sum() - e["cost"]) <= 1e-12 * e["cost"]
+    assert np.max(np.abs(rw.reshape(n, 2) - e["res"])) < 1e-12
+    Jc = Jw[:, 6 * F_:]
+    assert np.allclose(Jc.T @ Jc, e["U"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(Jc.T @ rw, e["gu"], rtol=1e-9, atol=1e-10)
+    for fi in range(F_):
+        rows = np.repeat(frame_of == fi, 2)
+        Jf = Jw[rows, 6 * fi:6 * fi + 6]
+        assert np.allclose(Jf.T @ Jf, e["V"][fi], rtol=1e-9, atol=1e-9)
+        assert np.allclose(Jf.T @ Jc[rows], e["W"][fi], rtol=1e-9, atol=1e-9)
+        assert np.allclose(Jf.T @ rw[rows], e["gv"][fi], rtol=1e-9, atol=1e-10)
